@@ -1,0 +1,182 @@
+/*
+ * spectralcluster_b200 -- C ABI of the B200-native SpectralClusterer.predict() hot path.
+ *
+ * The reference (wq2012/SpectralCluster v0.2.22) is pure Python and has no FFI:
+ * its drop-in boundary is the Python object surface.  This header
+ * is the boundary underneath our Python mirror of that surface: one entry point per
+ * reference operator, bound with ctypes by spectralcluster_b200/_native.py.  Every
+ * declaration cites the reference function (file:line under /root/reference) whose
+ * arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from sc_last_error() (thread local).
+ *   - all matrix pointers are DEVICE pointers (cudaMalloc'ed by the caller --
+ *     the Python host uses torch tensors purely as device buffers), row-major,
+ *     with an explicit leading dimension `ld` counted in elements.  fp32 matrices
+ *     need ld % 4 == 0 and 16-byte aligned bases; fp16 planes need ld % 8 == 0.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
+ *     asynchronous unless stated otherwise.
+ *   - "split fp16 planes" (hi, lo): value = hi + lo with hi = fp16(value),
+ *     lo = fp16(value - hi): the operand format of the tcgen05 GEMMs (three
+ *     kind::f16 MMAs hi*hi + hi*lo + lo*hi reproduce an fp32-accurate product).
+ */
+#ifndef SPECTRALCLUSTER_B200_H_
+#define SPECTRALCLUSTER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_ABI_VERSION 1
+
+/* enums mirror the reference's enum *names* (values are ours) */
+enum sc_threshold_type { SC_THRESHOLD_ROWMAX = 0, SC_THRESHOLD_PERCENTILE = 1 }; /* refinement.py:21-27 */
+enum sc_symmetrize_type { SC_SYMMETRIZE_MAX = 0, SC_SYMMETRIZE_AVERAGE = 1 };    /* refinement.py:30-36 */
+enum sc_laplacian_type {                                                          /* laplacian.py:9-21 */
+  SC_LAPLACIAN_AFFINITY = 0, SC_LAPLACIAN_UNNORMALIZED = 1,
+  SC_LAPLACIAN_RANDOMWALK = 2, SC_LAPLACIAN_GRAPHCUT = 3
+};
+enum sc_gemm_engine {
+  SC_GEMM_TCGEN05 = 0,   /* tcgen05.mma kind::f16 on split planes, TMA-fed (product path) */
+  SC_GEMM_SIMT_F64ACC = 1 /* SIMT fp32 operands, fp64 accumulation (validation path, small N) */
+};
+enum sc_gemm_precision {
+  SC_GEMM_SPLIT3 = 0,    /* hi*hi + hi*lo + lo*hi : ~2^-22 relative */
+  SC_GEMM_SINGLE = 1     /* hi*hi only            : ~2^-11 relative */
+};
+enum sc_which_end { SC_EIG_LARGEST = 0, SC_EIG_SMALLEST = 1 };
+
+typedef struct sc_context sc_context;
+
+int sc_abi_version(void);
+const char* sc_last_error(void);
+
+/* One context per (process, device).  Owns nothing the caller can see except
+ * cached device properties and stream-ordered scratch. */
+int sc_context_create(int device, sc_context** out);
+int sc_context_destroy(sc_context* ctx);
+int sc_context_sm_count(const sc_context* ctx);
+
+/* ---- utils.compute_affinity_matrix (utils.py:20-41) --------------------------------- */
+/* Row L2-normalisation (utils.py:32-33).  x is [n,d] fp32 (x_is_f64=0) or fp64 (=1) on the
+ * device.  Norms are accumulated in fp64.  Any of xn (fp32 [n,ldxn]) and hi/lo (fp16
+ * [n,ldh]) may be NULL.  Zero rows give NaN like the reference. */
+int sc_normalize_rows(sc_context* ctx, const void* x, int x_is_f64, int64_t n, int64_t d,
+                      int64_t ldx, float* xn, int64_t ldxn, void* hi, void* lo, int64_t ldh,
+                      void* stream);
+
+/* A = (Xn Xn^T + 1) / 2 (utils.py:35-39).  engine TCGEN05 reads the split planes,
+ * engine SIMT reads xn.  If rowmax_offdiag != NULL it receives max_j!=i A[i,j] clamped at 0
+ * (the CropDiagonal value, refinement.py:148-150) -- it must be zero-filled by the caller. */
+int sc_affinity_cosine(sc_context* ctx, int engine, int precision, const float* xn, int64_t ldxn,
+                       const void* hi, const void* lo, int64_t ldh, int64_t n, int64_t d,
+                       float* a, int64_t lda, float* rowmax_offdiag, void* stream);
+
+/* ---- refinement.py operators --------------------------------------------------------- */
+/* CropDiagonal.refine (refinement.py:145-151): out = a with diag[i] = max(0, max_{j!=i} a[i,j]).
+ * out may alias a. */
+int sc_crop_diagonal(sc_context* ctx, const float* a, int64_t n, int64_t lda, float* out,
+                     int64_t ldo, void* stream);
+
+/* Only the new diagonal of CropDiagonal (the vector the fused blur pass substitutes on read). */
+int sc_crop_diagonal_values(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                            float* diag_out, void* stream);
+
+/* GaussianBlur.refine (refinement.py:160-162) == scipy.ndimage.gaussian_filter(a, sigma):
+ * separable, axis 0 then axis 1, mode='reflect', truncate=4.0 (radius int(4*sigma+0.5)),
+ * weights computed in fp64.  sigma <= 1e-15 copies.  diag_override (may be NULL) replaces
+ * a[i,i] on read (fused CropDiagonal).  out == NULL runs the statistics-only pass.
+ * rowmax_out (may be NULL; caller zero-fills; values must be >= 0) receives max_j out[i,j]. */
+int sc_gaussian_blur(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                     const float* diag_override, double sigma, float* out, int64_t ldo,
+                     float* rowmax_out, void* stream);
+
+/* Statistics-only pass of the blur: rowmax_out[i] = max_j blur(a)[i,j], with the diagonal read
+ * as zero when zero_diagonal != 0 (RowWiseThreshold's preserve_diagonal, refinement.py:185-186). */
+int sc_gaussian_blur_rowmax(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                            const float* diag_override, double sigma, int zero_diagonal,
+                            float* rowmax_out, void* stream);
+
+/* RowWiseThreshold.refine (refinement.py:182-210), any option combination. */
+int sc_row_threshold(sc_context* ctx, const float* a, int64_t n, int64_t lda, int type, double p,
+                     double mult, int binarize, int preserve_diagonal, float* out, int64_t ldo,
+                     void* stream);
+
+/* Symmetrize.refine (refinement.py:219-226).  out must not alias a. */
+int sc_symmetrize(sc_context* ctx, const float* a, int64_t n, int64_t lda, int type, float* out,
+                  int64_t ldo, void* stream);
+
+/* Fused GaussianBlur -> RowWiseThreshold(RowMax) -> Symmetrize for a SYMMETRIC input
+ * (SURVEY.md A.3): y[i,j] = sym(t(b, m_i), t(b, m_j)), b = blur(a)[i,j], t = the threshold rule
+ * with row maxima `rowmax` (from the statistics-only pass of sc_gaussian_blur).  sigma <= 1e-15
+ * skips the blur.  Writes fp32 `y` and/or split planes (either may be NULL). */
+int sc_blur_threshold_symmetrize(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                                 const float* diag_override, double sigma, const float* rowmax,
+                                 double p, double mult, int binarize, int preserve_diagonal,
+                                 int sym_type, float* y, int64_t ldy, void* hi, void* lo,
+                                 int64_t ldh, void* stream);
+
+/* fp32 [n,n] -> split fp16 planes (for matrices that did not come out of the fused pass). */
+int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64_t lda, void* hi, void* lo,
+                    int64_t ldh, void* stream);
+
+/* Diffuse.refine (refinement.py:232-234): s = y y^T. */
+int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y, int64_t ldy,
+               const void* hi, const void* lo, int64_t ldh, int64_t n, float* s, int64_t lds,
+               void* stream);
+
+/* Row maxima and row sums (fp64) of an fp32 matrix: the reductions of
+ * RowWiseNormalize (refinement.py:243) and of the degree (laplacian.py:41). */
+int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda, double* rowmax,
+                 double* rowsum, void* stream);
+
+/* RowWiseNormalize.refine (refinement.py:240-245), materialised.  out may alias a. */
+int sc_row_normalize(sc_context* ctx, const float* a, int64_t n, int64_t lda, float* out,
+                     int64_t ldo, void* stream);
+
+/* ---- laplacian.compute_laplacian (laplacian.py:24-60), materialised in fp32 ----------- */
+int sc_laplacian(sc_context* ctx, const float* w, int64_t n, int64_t ldw, int type, double eps,
+                 float* out, int64_t ldo, void* stream);
+
+/* ---- utils.compute_sorted_eigenvectors (utils.py:44-71) ------------------------------ */
+/* The matrix decomposed is M = diag(delta) + sign * diag(left) S diag(right) with S symmetric
+ * fp32 and left,right > 0; delta/left/right are fp64 device vectors, NULL
+ * meaning zeros/ones/ones.  M is similar to the symmetric delta + sign * c S c, c = sqrt(left*
+ * right); reference eigenvectors are v = E u / |E u|, E = sqrt(left/right).
+ * Eigenvalues are returned sorted (descending for LARGEST, ascending for SMALLEST) in
+ * w_host[0..n_values); unit-norm eigenvectors of M for the first n_vectors of them go to
+ * v_dev, fp64 row-major [n, n_vectors].  SYNCHRONOUS (returns after the stream drains).
+ *
+ * sc_eigh_dense: Householder tridiagonalisation + implicit QL, all in fp64 on the device, full
+ * spectrum (n_values <= n).  sc_eigh_extremal: thick-restart Lanczos on the implicit operator
+ * (fp32 S streamed from HBM, fp64 vectors), n_values << n. */
+int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t lds, const double* delta,
+                  const double* left, const double* right, double sign, int which,
+                  int64_t n_values, int64_t n_vectors, double* w_host, double* v_dev,
+                  void* stream);
+int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds, const double* delta,
+                     const double* left, const double* right, double sign, int which,
+                     int64_t n_values, int64_t n_vectors, double tol, int64_t max_matvecs,
+                     double* w_host, double* v_dev, int64_t* stats_host, void* stream);
+
+/* Rows of e[n,k] (fp64) scaled to unit L2 norm (spectral_clusterer.py:301-305). In place. */
+int sc_row_renorm(sc_context* ctx, double* e, int64_t n, int64_t k, void* stream);
+
+/* ---- custom_distance_kmeans.run_kmeans (custom_distance_kmeans.py:13-52, 85-141) ------ */
+/* e is fp64 [n,k_dim] on the device.  Seeding = scikit-learn KMeans(init="k-means++",
+ * max_iter=1, random_state=0, n_init="auto") restated on the device: `first_center` and the
+ * uniform draws u[(k-1)*trials] come from the caller's np.random.RandomState(0) (host RNG
+ * logic only).  metric 0 = cosine, 1 = euclidean.  labels_host int64[n].  SYNCHRONOUS.
+ * iters_host (may be NULL) receives the number of assignment passes. */
+int sc_kmeans(sc_context* ctx, const double* e, int64_t n, int64_t k_dim, int64_t k,
+              int64_t first_center, const double* u_host, int64_t trials, int metric,
+              int64_t max_iter, double tol, int64_t* labels_host, int64_t* iters_host,
+              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRALCLUSTER_B200_H_ */

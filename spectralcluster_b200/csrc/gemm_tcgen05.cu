@@ -1,0 +1,415 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (both operands K-major),
+// the only two dense contractions of the hot path:
+//   utils.py:35-39        affinity = (Xn Xn^T + 1)/2        K = d      (EPI_AFFINITY)
+//   refinement.py:232-234 Diffuse  = Y Y^T                  K = N      (EPI_PLAIN)
+//
+// Operands are "split fp16 planes" (value = hi + lo).  Per 64-wide K block the MMA warp issues
+//     D += Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi          (tcgen05.mma kind::f16, fp32 accum)
+// which reproduces the fp32 product to ~2^-22 relative (the dropped lo*lo term is 2^-22) at the
+// fp16 tensor-pipe rate; SC_GEMM_SINGLE issues only the first (2^-11).
+//
+// Structure (one CTA per SM, persistent, 256 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 (or 2) planes of a
+//            K block into a ring of stages, completion on an mbarrier (expect_tx)
+//   warp 1   MMA issuer: one lane issues tcgen05.mma M=128 N=256 K=16 from shared-memory
+//            descriptors into a TMEM accumulator (128 lanes x 256 fp32 columns), frees the
+//            stage with tcgen05.commit
+//   warp 2   TMEM allocator (512 columns = two accumulators, so the epilogue of tile t overlaps
+//            the main loop of tile t+1)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (thread = accumulator row), fused (x+1)/2 and
+//            off-diagonal row maximum for the affinity, 128-bit global stores
+// Tiles are rasterised in groups of 16 M-blocks so that a wave of 148 CTAs shares
+// 16 A-panels and ~9 B-panels through L2.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace sc {
+
+constexpr int BM = 128, BN = 256, BK = 64;          // BK fp16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_PLANE_BYTES = BN * BK * 2;           // 32 KB
+constexpr int GROUP_M = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;            // trap instead of hanging the GPU
+
+enum { TC_EPI_PLAIN = 0, TC_EPI_AFFINITY = 1 };
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int32_t c_inner, int32_t c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B
+// between 8-row groups | version [46,48) = 1 | layout [61,64) = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=F16 [7,10)=0,
+// B=F16 [10,13)=0, both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TileCoord {
+  int m_blk, n_blk;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles_n) {
+  const int group = GROUP_M * tiles_n;
+  const int g = tile / group;
+  const int first_m = g * GROUP_M;
+  const int gm = min(GROUP_M, tiles_m - first_m);
+  const int r = tile - g * group;
+  TileCoord t;
+  t.m_blk = first_m + r % gm;
+  t.n_blk = r / gm;
+  return t;
+}
+
+template <bool SPLIT, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
+               const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi,
+               const __grid_constant__ CUtensorMap map_b_lo, int M, int N, int K,
+               float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag) {
+  constexpr int STAGES = SPLIT ? 2 : 4;
+  constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+    if (SPLIT) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);      // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(tile, tiles_m, tiles_n);
+        const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+          mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
+          const int k0 = kb * BK;
+          tma_load_2d(base, &map_a_hi, bar, k0, row_a);
+          tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
+          if (SPLIT) {
+            tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
+            tma_load_2d(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_b_lo, bar, k0, row_b);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);   // epilogue drained this buffer
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(base);
+          const uint64_t b_hi = make_smem_desc(base + A_PLANE_BYTES);
+          const uint64_t a_lo = make_smem_desc(base + A_PLANE_BYTES + B_PLANE_BYTES);
+          const uint64_t b_lo = make_smem_desc(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the >>4 address
+            const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
+            umma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+            if (SPLIT) {
+              umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));      // stage reusable when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));          // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (TMEM -> regs -> global)
+    const int quad = warp & 3;                            // TMEM lanes 32*quad .. +31
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(tile, tiles_m, tiles_n);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = (int64_t)tc.m_blk * BM + quad * 32 + lane;
+      const int64_t col0 = (int64_t)tc.n_blk * BN;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16);
+      float rmax = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (row < M) {
+          float* dst = C + row * ldc + col0 + c * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int64_t col = col0 + c * 32 + q * 4;
+            float f[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float x = __uint_as_float(v[q * 4 + t]);
+              if (EPI == TC_EPI_AFFINITY) {
+                x = (x + 1.0f) * 0.5f;                    // utils.py:39
+                if (col + t != row && col + t < N) rmax = fmaxf(rmax, x);
+              }
+              f[t] = x;
+            }
+            if (col + 3 < N) {
+              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (col + t < N) dst[q * 4 + t] = f[t];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (EPI == TC_EPI_AFFINITY && rowmax_offdiag && row < M)
+        atomic_max_nonneg(rowmax_offdiag + row, rmax);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp16 tensor [rows, k] with leading dimension ld (elements); box = BK x box_rows.
+static int make_plane_map(CUtensorMap* map, const __half* ptr, int64_t rows, int64_t k,
+                          int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  SC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+             "tcgen05 GEMM: fp16 planes need 16-byte aligned base and ld %% 8 == 0");
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <bool SPLIT, int EPI>
+static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
+                  const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
+                  int64_t ldc, float* rowmax, cudaStream_t st) {
+  constexpr int STAGES = SPLIT ? 2 : 4;
+  constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  SC_REQUIRE(smem <= ctx->smem_optin, "tcgen05 GEMM needs %zu B of shared memory", smem);
+  auto kern = k_gemm_tcgen05<SPLIT, EPI>;
+  SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  kern<<<grid, NUM_THREADS, smem, st>>>(ah, al, bh, bl, M, N, K, C, ldc, rowmax);
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
+                    const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
+                    int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                    float* rowmax_offdiag, cudaStream_t st) {
+  SC_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31),
+             "tcgen05 GEMM: bad shape");
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0,
+             "tcgen05 GEMM: C needs a 16-byte aligned base and ldc %% 4 == 0");
+  const bool split = (precision == SC_GEMM_SPLIT3);
+  CUtensorMap ah, al, bh, bl;
+  if (int r = make_plane_map(&ah, a_hi, M, K, lda, BM)) return r;
+  if (int r = make_plane_map(&bh, b_hi, N, K, ldb, BN)) return r;
+  if (split) {
+    if (int r = make_plane_map(&al, a_lo, M, K, lda, BM)) return r;
+    if (int r = make_plane_map(&bl, b_lo, N, K, ldb, BN)) return r;
+  } else {
+    al = ah;
+    bl = bh;
+  }
+  if (split) {
+    if (epi == TC_EPI_AFFINITY)
+      return launch<true, TC_EPI_AFFINITY>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
+                                           rowmax_offdiag, st);
+    return launch<true, TC_EPI_PLAIN>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
+                                      nullptr, st);
+  }
+  if (epi == TC_EPI_AFFINITY)
+    return launch<false, TC_EPI_AFFINITY>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
+                                          rowmax_offdiag, st);
+  return launch<false, TC_EPI_PLAIN>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc, nullptr,
+                                     st);
+}
+
+}  // namespace sc

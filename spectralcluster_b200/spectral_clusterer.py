@@ -1,0 +1,222 @@
+"""SpectralClusterer -- drop-in mirror of the reference orchestrator
+(/root/reference/spectralcluster/spectral_clusterer.py: __init__ :29-106,
+_compute_eigenvectors_ncluster :108-168, predict :201-314) whose arithmetic runs on a B200.
+
+predict(): one H2D copy of the [N, d] embeddings, every N x N intermediate stays in HBM
+(affinity GEMM -> fused refinement -> Diffuse GEMM -> row statistics -> symmetric eigensolve ->
+k-means), one D2H copy of N labels.  Branches of the reference that leave the hot path
+(fallback clusterer, max_spectral_size pre-clustering, constraints, single-cluster checks,
+non-symmetrisable eigenproblems) raise NotImplementedError instead of falling back to a CPU.
+"""
+
+from __future__ import annotations
+
+import typing
+
+import numpy as np
+
+from . import _native as nat
+from . import autotune as autotune_lib
+from . import custom_distance_kmeans
+from . import device as dev
+from . import fallback_clusterer
+from . import laplacian as laplacian_lib
+from . import refinement
+from . import utils
+
+AutoTune = autotune_lib.AutoTune
+AutoTuneProxy = autotune_lib.AutoTuneProxy
+FallbackOptions = fallback_clusterer.FallbackOptions
+LaplacianType = laplacian_lib.LaplacianType
+RefinementName = refinement.RefinementName
+RefinementOptions = refinement.RefinementOptions
+EigenGapType = utils.EigenGapType
+
+
+class DeviceAffinity:
+  """An affinity matrix resident in HBM (what predict() passes between its stages)."""
+
+  def __init__(self, matrix, n: int, crop_vector=None, symmetric: bool = True):
+    self.matrix = matrix
+    self.n = n
+    self.crop_vector = crop_vector
+    self.symmetric = symmetric
+
+
+class SpectralClusterer:
+  """Spectral clustering of embeddings; same constructor and attributes as the reference."""
+
+  def __init__(self,
+               min_clusters: typing.Optional[int] = None,
+               max_clusters: typing.Optional[int] = None,
+               refinement_options: typing.Optional[RefinementOptions] = None,
+               autotune: typing.Optional[AutoTune] = None,
+               fallback_options: typing.Optional[FallbackOptions] = None,
+               laplacian_type: typing.Optional[LaplacianType] = None,
+               stop_eigenvalue: float = 1e-2,
+               row_wise_renorm: bool = False,
+               custom_dist: typing.Union[str, typing.Callable] = "cosine",
+               max_iter: int = 300,
+               constraint_options=None,
+               eigengap_type: EigenGapType = EigenGapType.Ratio,
+               max_spectral_size: typing.Optional[int] = None,
+               affinity_function: typing.Callable = utils.compute_affinity_matrix,
+               post_eigen_cluster_function: typing.Callable = (
+                   custom_distance_kmeans.run_kmeans)):
+    self.min_clusters = min_clusters
+    self.max_clusters = max_clusters
+    self.refinement_options = refinement_options or RefinementOptions()
+    self.autotune = autotune
+    self.fallback_options = fallback_options or FallbackOptions()
+    self.laplacian_type = laplacian_type
+    self.row_wise_renorm = row_wise_renorm
+    self.stop_eigenvalue = stop_eigenvalue
+    self.custom_dist = custom_dist
+    self.max_iter = max_iter
+    self.constraint_options = constraint_options
+    self.eigengap_type = eigengap_type
+    self.max_spectral_size = max_spectral_size
+    self.affinity_function = affinity_function
+    self.post_eigen_cluster_function = post_eigen_cluster_function
+    # Diagnostics of the last predict(): eigenvalues used by the eigengap, cluster count, solver.
+    self.last_details: typing.Dict[str, typing.Any] = {}
+
+  # ------------------------------------------------------------------ eigen stage
+  def _eigen_on_device(self, eng, affinity: DeviceAffinity):
+    """Refinement + Laplacian terms + eigensolve; returns (w host, V device [n, nv], k, gap)."""
+    n = affinity.n
+    refined = dev.run_refinement(eng, affinity.matrix, n, self.refinement_options,
+                                 crop_vector=affinity.crop_vector,
+                                 a_symmetric=affinity.symmetric)
+    if not refined.symmetric:
+      raise NotImplementedError(
+          "this refinement sequence leaves a matrix that is not symmetric or diagonally similar "
+          "to a symmetric one; the general eigensolver is outside the B200 hot path "
+          "(SURVEY.md 8(f) rank 1)")
+    delta, left, right, sign, which = laplacian_lib.operator_terms(eng, refined,
+                                                                   self.laplacian_type)
+    descend = which == nat.EIG_LARGEST
+    limit = n
+    if self.max_clusters and self.max_clusters + 1 < limit:
+      limit = self.max_clusters + 1
+    n_vectors = min(n, max(limit, self.min_clusters or 0))
+    dense = (n <= eng.dense_eig_max) or not self.max_clusters or limit > 32
+    if dense:
+      w, v, stats = eng.eigh(refined.s, n, delta, left, right, sign, which, n, n_vectors, True)
+    else:
+      w, v, stats = eng.eigh(refined.s, n, delta, left, right, sign, which, limit, n_vectors,
+                             False)
+      if not descend and self.eigengap_type == EigenGapType.NormalizedDiff:
+        # np.max(eigenvalues) of the full spectrum (utils.py:109): one more extremal solve
+        top, _, _ = eng.eigh(refined.s, n, delta, left, right, sign, nat.EIG_LARGEST, 1, 0, False)
+        w = np.concatenate([w, top])
+    if descend:
+      k, gap = utils.compute_number_of_clusters(
+          w, max_clusters=self.max_clusters, stop_eigenvalue=self.stop_eigenvalue,
+          eigengap_type=self.eigengap_type, descend=True)
+    else:
+      k, gap = utils.compute_number_of_clusters(
+          w, max_clusters=self.max_clusters, eigengap_type=self.eigengap_type, descend=False)
+    self.last_details = dict(eigenvalues=np.array(w[:limit]), n_clusters_raw=k, max_gap=gap,
+                             solver="dense" if dense else "lanczos",
+                             lanczos_stats=None if dense else stats.tolist())
+    return w, v, k, gap
+
+  def _compute_eigenvectors_ncluster(self, affinity, constraint_matrix=None):
+    """(eigenvectors, n_clusters, max eigengap) for an affinity matrix.
+
+    `affinity` is a host ndarray (reference signature) or a DeviceAffinity.  Eigenvectors come
+    back as a host ndarray [n, n_vec] in the first case, a device fp64 tensor in the second;
+    n_vec covers every column predict() can select (all n when max_clusters is None)."""
+    if constraint_matrix is not None and self.constraint_options:
+      raise NotImplementedError("constraints are outside the B200 hot path (SURVEY.md section 2)")
+    eng = dev.Engine.get()
+    if isinstance(affinity, DeviceAffinity):
+      _, v, k, gap = self._eigen_on_device(eng, affinity)
+      return v, k, gap
+    a = np.asarray(affinity)
+    if a.ndim != 2:
+      raise ValueError("affinity must be 2-dimensional")
+    if a.shape[0] != a.shape[1]:
+      raise ValueError("affinity must be a square matrix")
+    sym = bool(np.allclose(a, a.T, rtol=1e-6, atol=1e-9))
+    da = DeviceAffinity(eng.upload_matrix(a), a.shape[0], None, sym)
+    _, v, k, gap = self._eigen_on_device(eng, da)
+    return v.to("cpu").numpy(), k, gap
+
+  # ------------------------------------------------------------------ predict
+  def predict(self, embeddings: np.ndarray, constraint_matrix=None) -> np.ndarray:
+    """Cluster the rows of `embeddings` ([n_samples, n_features] ndarray) -> int64 labels."""
+    num_embeddings = embeddings.shape[0]
+    if not isinstance(embeddings, np.ndarray):
+      raise TypeError("embeddings must be a numpy array")
+    if len(embeddings.shape) != 2:
+      raise ValueError("embeddings must be 2-dimensional")
+    if num_embeddings < self.fallback_options.spectral_min_embeddings:
+      raise NotImplementedError("the fallback clusterer is outside the B200 hot path")
+    if self.max_spectral_size is not None and num_embeddings > self.max_spectral_size:
+      if constraint_matrix is not None:
+        raise RuntimeError("Cannot handle constraint_matrix when max_spectral_size is set")
+      if (self.max_spectral_size < 2 or
+          (self.max_clusters and self.max_spectral_size <= self.max_clusters) or
+          (self.min_clusters and self.max_spectral_size <= self.min_clusters)):
+        raise ValueError("max_spectral_size should be a relatively big number")
+      raise NotImplementedError(
+          "max_spectral_size pre-clustering (AHC) is outside the B200 hot path; the B200 path "
+          "handles the full N exactly")
+    if self.min_clusters == 1:
+      raise NotImplementedError("single-cluster detection is outside the B200 hot path")
+    if constraint_matrix is not None and self.constraint_options:
+      raise NotImplementedError("constraints are outside the B200 hot path")
+
+    eng = dev.Engine.get()
+    t = dev.torch()
+    sequence = list(self.refinement_options.refinement_sequence or [])
+    if self.affinity_function is utils.compute_affinity_matrix:
+      x = np.ascontiguousarray(embeddings)
+      if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float64)
+      x_dev = t.from_numpy(x).to(eng.device, non_blocking=True)
+      crop_first = bool(sequence) and sequence[0] == RefinementName.CropDiagonal
+      a, crop = eng.affinity(x_dev, want_crop_vector=crop_first)
+      affinity = DeviceAffinity(a, num_embeddings, crop, True)
+    else:
+      host = np.asarray(self.affinity_function(embeddings))
+      affinity = DeviceAffinity(eng.upload_matrix(host), num_embeddings, None,
+                                bool(np.allclose(host, host.T, rtol=1e-6, atol=1e-9)))
+
+    if self.autotune:
+      if RefinementName.RowWiseThreshold not in sequence:
+        raise ValueError("AutoTune is only effective when the refinement sequence"
+                         "contains RowWiseThreshold")
+      proxy = self.autotune.proxy
+
+      def p_percentile_to_ratio(p_percentile: float):
+        self.refinement_options.p_percentile = p_percentile   # shared state, as the reference
+        vectors, k, gap = self._compute_eigenvectors_ncluster(affinity)
+        if proxy == AutoTuneProxy.PercentileSqrtOverNME:
+          return np.sqrt(1 - p_percentile) / gap, vectors, k
+        if proxy == AutoTuneProxy.PercentileOverNME:
+          return (1 - p_percentile) / gap, vectors, k
+        raise ValueError("Unsupported value of AutoTuneProxy")
+
+      eigenvectors, n_clusters, best_p = self.autotune.tune(p_percentile_to_ratio)
+      self.last_details["best_p_percentile"] = best_p
+    else:
+      eigenvectors, n_clusters, _ = self._compute_eigenvectors_ncluster(affinity)
+    del affinity
+
+    if self.min_clusters is not None:
+      n_clusters = max(n_clusters, self.min_clusters)
+    self.last_details["n_clusters"] = n_clusters
+
+    spectral = eigenvectors[:, :n_clusters].contiguous()
+    if self.row_wise_renorm and n_clusters > 0:
+      eng.row_renorm(spectral)
+    if self.post_eigen_cluster_function is custom_distance_kmeans.run_kmeans:
+      return custom_distance_kmeans.run_kmeans(
+          spectral_embeddings=spectral, n_clusters=n_clusters, custom_dist=self.custom_dist,
+          max_iter=self.max_iter)
+    return self.post_eigen_cluster_function(
+        spectral_embeddings=spectral.to("cpu").numpy(), n_clusters=n_clusters,
+        custom_dist=self.custom_dist, max_iter=self.max_iter)
