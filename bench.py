@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the SpectralClusterer.predict() hot path (BASELINE.json metric:
+embeddings/sec through predict() at N=65,536 d=256; eigensolve ms).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 65536]
+
+One "step" = one predict() over one batch of N synthetic speaker-turn d-vectors
+(SURVEY.md 8(d)).  Workload (BASELINE.json configs[2], the configuration the metric is quoted
+on): N=65,536, d=256, ICASSP-2018 refinement sequence, GraphCut Laplacian, eigengap in [2,10].
+
+  value : embeddings/s with the embeddings already resident in HBM (CUDA events)
+  e2e   : the same metric through the public API -- predict(np.ndarray) -> np.ndarray, the H2D
+          copy of the embeddings and the D2H copy of the labels inside the timed region
+  roofline : the dominant kernel (Diffuse, tcgen05 GEMM) against the measured tensor peak
+  cpu_baseline / --impl reference : the NumPy/SciPy/scikit-learn oracle (a restatement of the
+          pure-Python reference, which cannot travel to the GPU box) on a bounded sample
+
+With --gpus N > 1 (torchrun) every rank clusters its own independent batch (weak scaling,
+replicas; the path has no data-path collective at this N -- see DESIGN.md "Multi-GPU").
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--n", type=int, default=65536)
+  ap.add_argument("--d", type=int, default=256)
+  ap.add_argument("--speakers", type=int, default=6)
+  ap.add_argument("--cpu-sample-n", type=int, default=2048)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+def workload_name(n, d):
+  return ("N=%d d=%d synthetic speaker-turn d-vectors; ICASSP2018 refinement "
+          "(Crop,Blur,RowMax-Threshold,Symmetrize,Diffuse,RowNormalize) + GraphCut Laplacian + "
+          "eigengap k in [2,10] + cosine k-means" % (n, d))
+
+
+def oracle_options():
+  from oracle import spectral_oracle as orc
+  return orc.options(min_clusters=2, max_clusters=10, sequence=orc.ICASSP2018,
+                     laplacian="graphcut")
+
+
+def make_clusterer():
+  import spectralcluster_b200 as scb
+  return scb.SpectralClusterer(
+      min_clusters=2, max_clusters=10, laplacian_type=scb.LaplacianType.GraphCut,
+      refinement_options=scb.RefinementOptions(
+          gaussian_blur_sigma=1, p_percentile=0.95, thresholding_soft_multiplier=0.01,
+          thresholding_type=scb.ThresholdType.RowMax,
+          refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE)),
+      custom_dist="cosine")
+
+
+class ClockSampler(threading.Thread):
+  """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index = index
+    self.rows = []
+    self.stop_flag = threading.Event()
+
+  def run(self):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    while not self.stop_flag.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if out:
+          self.rows.append([c.strip() for c in out.split(",")])
+      except Exception:
+        pass
+      self.stop_flag.wait(0.2)
+
+  def summary(self):
+    if not self.rows:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names)
+               if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+            "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(sample_n, d, speakers, repeats=1):
+  """Oracle predict() (NumPy/OpenBLAS, SciPy, scikit-learn; all host cores) on a bounded
+  sample of the same workload.  eig is ~N^3, so the full N=65,536 is out of reach of the CPU
+  path (>=137 GB and ~19 h); the sample size is reported."""
+  from oracle import spectral_oracle as orc
+  x = orc.synthetic_dvectors(sample_n, d, speakers, seed=0)
+  opt = oracle_options()
+  best = None
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    orc.predict(x, opt)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  try:
+    import threadpoolctl
+    threads = max((p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()), default=1)
+  except Exception:
+    threads = os.cpu_count()
+  return {"value": sample_n / best, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
+          "sample": "oracle predict() on N=%d d=%d of the same generator (%.2f s); the CPU path "
+                    "scales ~N^3 and cannot run N=65,536" % (sample_n, d, best),
+          "seconds": best}
+
+
+def run_reference(args, rank):
+  if rank != 0:
+    return
+  total = args.warmup + args.steps
+  from oracle import spectral_oracle as orc
+  x = orc.synthetic_dvectors(args.cpu_sample_n, args.d, args.speakers, seed=0)
+  opt = oracle_options()
+  times = []
+  for i in range(total):
+    t0 = time.perf_counter()
+    orc.predict(x, opt)
+    times.append(time.perf_counter() - t0)
+  timed = times[args.warmup:]
+  sec = sum(timed) / len(timed)
+  val = args.cpu_sample_n / sec
+  try:
+    import threadpoolctl
+    threads = max((p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()), default=1)
+  except Exception:
+    threads = os.cpu_count()
+  line = {
+      "impl": "reference", "metric": "embeddings/sec through predict()", "value": val,
+      "unit": "embeddings/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+      "config": {"workload": workload_name(args.n, args.d),
+                 "sample": "each step = the CPU path on N=%d of the same generator" % args.cpu_sample_n},
+      "cpu_baseline": {"value": val, "unit": "embeddings/s", "cores": int(threads),
+                       "kind": "port",
+                       "sample": "oracle (NumPy/SciPy/scikit-learn restatement of the pure-Python "
+                                 "reference) predict() on N=%d d=%d per step" % (args.cpu_sample_n, args.d)},
+      "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+def main():
+  args = parse()
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  if args.impl == "reference":
+    run_reference(args, rank)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from oracle import spectral_oracle as orc
+  from spectralcluster_b200 import _native as nat
+  from spectralcluster_b200 import device as dev
+
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  eng = dev.Engine.get(local_rank)
+  n, d = args.n, args.d
+  # every rank clusters its own batch (different seed): weak scaling over independent units
+  x = orc.synthetic_dvectors(n, d, args.speakers, seed=rank).astype(np.float32)
+  x_pinned = torch.from_numpy(x).pin_memory()
+  clusterer = make_clusterer()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---------------- e2e: host ndarray in, host labels out
+  labels = None
+  for _ in range(args.warmup):
+    labels = clusterer.predict(x_pinned.numpy())
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    labels = clusterer.predict(x_pinned.numpy())
+  barrier()
+  e2e_s = time.perf_counter() - t0
+  k_found = clusterer.last_details.get("n_clusters")
+
+  # ---------------- device-resident: embeddings already in HBM, CUDA events
+  from spectralcluster_b200 import spectral_clusterer as sc_mod
+  x_dev = torch.from_numpy(x).to(eng.device)
+  seq = clusterer.refinement_options.refinement_sequence
+
+  def device_step():
+    a, crop = eng.affinity(x_dev, want_crop_vector=True)
+    aff = sc_mod.DeviceAffinity(a, n, crop, True)
+    v, k, _ = clusterer._compute_eigenvectors_ncluster(aff)
+    k = max(k, clusterer.min_clusters)
+    emb = v[:, :k].contiguous()
+    return eng.kmeans(emb, k, 0, clusterer.max_iter)[0]
+
+  for _ in range(max(1, args.warmup - 2)):     # the e2e loop above already warmed everything
+    device_step()
+  barrier()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  launches0 = nat.load().sc_launch_count()
+  eng.start_profile()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  start.record()
+  for _ in range(args.steps):
+    device_step()
+  stop.record()
+  barrier()
+  dev_ms = start.elapsed_time(stop)
+  stages = eng.stop_profile()
+  launches = nat.load().sc_launch_count() - launches0
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+
+  if world > 1:
+    tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(tt[0]), float(tt[1])
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  ms_per_step = dev_ms / args.steps
+  value = world * n / (ms_per_step / 1e3)
+  e2e_value = world * n * args.steps / e2e_s
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    pass
+  tensor_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+  peak_note = "measured (MEASURED_PEAKS.json, sustained fp16/bf16 dense)" if peaks else \
+      "fallback (B200_PROFILING.md sustained)"
+  diffuse_ms = stages.get("sc_diffuse", 0.0) / args.steps
+  flops = 2.0 * n * n * n           # algorithmic: full product Y Y^T
+  achieved = flops / (diffuse_ms * 1e-3) / 1e12 if diffuse_ms > 0 else None
+  hbm_peak = peaks.get("hbm_gbs") or 6650.0
+  line = {
+      "metric": "embeddings/sec through predict()", "value": value, "unit": "embeddings/s",
+      "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32 storage; fp16x3 split tensor-core products with f32 accumulate; f64 eigensolve and k-means",
+      "data": "synthetic",
+      "config": {"workload": workload_name(n, d), "l2": "inputs larger than L2 (N x N fp32 = %.1f GB)"
+                 % (n * n * 4 / 1e9), "parallelism": "replicas x%d" % world,
+                 "clusters_found": k_found,
+                 "eigensolver": clusterer.last_details.get("solver"),
+                 "lanczos_stats[matvecs,restarts,converged,m]": clusterer.last_details.get("lanczos_stats")},
+      "e2e": {"value": e2e_value, "unit": "embeddings/s", "h2d_bytes_per_step": int(x.nbytes),
+              "d2h_bytes_per_step": int(labels.nbytes) + 8 * 16},
+      "gpu_launches": int(launches),
+      "eigensolve_ms": (stages.get("sc_eigh_extremal", 0.0) + stages.get("sc_eigh_dense", 0.0)) / args.steps,
+      "stage_ms": {k: v / args.steps for k, v in sorted(stages.items())},
+      "roofline": {"kernel": "k_gemm_tcgen05 (Diffuse, Y Y^T)", "bound": "tensor",
+                   "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                   "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                   "peak_source": peak_note,
+                   "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse; the "
+                           "kernel issues 3x that in fp16 MMAs (hi*hi + hi*lo + lo*hi)"},
+      "roofline_hbm_stages": {
+          "blur_stats_pass_GBps": (n * n * 4 / 1e9) / (stages.get("sc_gaussian_blur_rowmax", 0) / args.steps / 1e3)
+          if stages.get("sc_gaussian_blur_rowmax") else None,
+          "blur_thrsym_pass_GBps": (n * n * 8 / 1e9) / (stages.get("sc_blur_threshold_symmetrize", 0) / args.steps / 1e3)
+          if stages.get("sc_blur_threshold_symmetrize") else None,
+          "peak_GBps": hbm_peak},
+      "clocks": sampler.summary(),
+  }
+  if not args.no_cpu_baseline:
+    line["cpu_baseline"] = cpu_baseline(args.cpu_sample_n, d, args.speakers)
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

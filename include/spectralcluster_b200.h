@@ -53,6 +53,8 @@ typedef struct sc_context sc_context;
 
 int sc_abi_version(void);
 const char* sc_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+long long sc_launch_count(void);
 
 /* One context per (process, device).  Owns nothing the caller can see except
  * cached device properties and stream-ordered scratch. */

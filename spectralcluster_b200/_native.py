@@ -23,6 +23,7 @@ c_ptr = ctypes.c_void_p
 PROTOTYPES = {
     "sc_abi_version": [],
     "sc_last_error": [],
+    "sc_launch_count": [],
     "sc_context_create": [c_int, ctypes.POINTER(c_ptr)],
     "sc_context_destroy": [c_ptr],
     "sc_context_sm_count": [c_ptr],
@@ -85,7 +86,8 @@ def load():
     for name, args in PROTOTYPES.items():
       fn = getattr(lib, name)
       fn.argtypes = args
-      fn.restype = ctypes.c_char_p if name == "sc_last_error" else ctypes.c_int
+      fn.restype = (ctypes.c_char_p if name == "sc_last_error" else
+                    ctypes.c_longlong if name == "sc_launch_count" else ctypes.c_int)
     if lib.sc_abi_version() != 1:
       raise ImportError("spectralcluster_b200: ABI version mismatch")
     _lib = lib

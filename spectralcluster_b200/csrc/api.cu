@@ -1,6 +1,7 @@
 // Context, error reporting and the GEMM-backed entry points of the C ABI.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <string>
 
@@ -14,6 +15,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void launched(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // gemm_simt.cu
 int gemm_nt_simt(int epi, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
@@ -32,6 +36,8 @@ using namespace sc;
 extern "C" int sc_abi_version(void) { return SC_ABI_VERSION; }
 
 extern "C" const char* sc_last_error(void) { return g_error; }
+
+extern "C" long long sc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int sc_context_create(int device, sc_context** out) {
   SC_REQUIRE(out != nullptr, "sc_context_create: out is NULL");

@@ -244,7 +244,7 @@ template <int EPI>
 static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStream_t st) {
   if (sigma <= 1e-15) {     // scipy: "if sigma > 1e-15 ... else output[...] = input[...]"
     const unsigned gy = (unsigned)std::min<int64_t>((g.n + 1023) / 1024, 64);
-    k_noblur<EPI><<<dim3((unsigned)g.n, gy), 256, 0, st>>>(g);
+    k_noblur<EPI><<<dim3((unsigned)g.n, gy), 256, 0, st>>>(g); sc::launched();
     SC_LAUNCH_CHECK();
     return 0;
   }
@@ -255,7 +255,7 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
   g.radius = radius;
   if (radius == 0) {        // a single tap of weight 1
     const unsigned gy = (unsigned)std::min<int64_t>((g.n + 1023) / 1024, 64);
-    k_noblur<EPI><<<dim3((unsigned)g.n, gy), 256, 0, st>>>(g);
+    k_noblur<EPI><<<dim3((unsigned)g.n, gy), 256, 0, st>>>(g); sc::launched();
     SC_LAUNCH_CHECK();
     return 0;
   }
@@ -266,7 +266,7 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
     auto kern = k_blur_tile<R, EPI>;
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 grid((unsigned)((g.n + TTW - 1) / TTW), (unsigned)((g.n + TTH - 1) / TTH));
-    kern<<<grid, TTHREADS, smem, st>>>(g, bw);
+    kern<<<grid, TTHREADS, smem, st>>>(g, bw); sc::launched();
     SC_LAUNCH_CHECK();
     return 0;
   }
@@ -276,7 +276,7 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
   auto kern = k_blur_generic<EPI>;
   SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((unsigned)((g.n + GTW - 1) / GTW), (unsigned)((g.n + GTH - 1) / GTH));
-  kern<<<grid, GTHREADS, smem, st>>>(g, bw);
+  kern<<<grid, GTHREADS, smem, st>>>(g, bw); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

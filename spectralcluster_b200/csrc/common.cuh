@@ -20,6 +20,7 @@ struct sc_context {
 namespace sc {
 
 void set_error(const char* fmt, ...);
+void launched(int n = 1);   // bumps the process-wide kernel launch counter (sc_launch_count)
 
 #define SC_CUDA(expr)                                                                   \
   do {                                                                                  \

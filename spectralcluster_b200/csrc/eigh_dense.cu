@@ -317,18 +317,18 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
 
   const unsigned gy = (unsigned)std::min<int64_t>((n + 255) / 256, 64);
   k_build_sym<<<dim3((unsigned)n, gy), 256, 0, st>>>(s, n, lds, delta, left, right, sign,
-                                                    T.as<double>());
+                                                    T.as<double>()); sc::launched();
   SC_LAUNCH_CHECK();
   for (int64_t j = 0; j + 2 < n; ++j) {
     const int64_t m = n - j - 1;
-    k_hh_reflector<<<1, 512, 0, st>>>(T.as<double>(), n, j, d, e, tau, vbuf);
-    k_hh_symv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(T.as<double>(), n, j, vbuf, pbuf);
-    k_hh_w<<<1, 512, 0, st>>>(tau, j, m, vbuf, pbuf, wbuf);
+    k_hh_reflector<<<1, 512, 0, st>>>(T.as<double>(), n, j, d, e, tau, vbuf); sc::launched();
+    k_hh_symv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(T.as<double>(), n, j, vbuf, pbuf); sc::launched();
+    k_hh_w<<<1, 512, 0, st>>>(tau, j, m, vbuf, pbuf, wbuf); sc::launched();
     k_hh_rank2<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, st>>>(T.as<double>(), n,
-                                                                                j, vbuf, wbuf);
+                                                                                j, vbuf, wbuf); sc::launched();
   }
   SC_LAUNCH_CHECK();
-  k_hh_tail<<<1, 32, 0, st>>>(T.as<double>(), n, d, e, tau);
+  k_hh_tail<<<1, 32, 0, st>>>(T.as<double>(), n, d, e, tau); sc::launched();
   SC_LAUNCH_CHECK();
 
   SC_CUDA(rc.alloc(sizeof(double) * (size_t)rot_cap, st));
@@ -336,7 +336,7 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
   SC_CUDA(sw.alloc(sizeof(Sweep) * (size_t)sweep_cap, st));
   SC_CUDA(stat.alloc(sizeof(QlStatus), st));
   k_tql_rotations<<<1, 32, 0, st>>>(d, e, (int)n, rc.as<double>(), rs.as<double>(), rot_cap,
-                                    sw.as<Sweep>(), sweep_cap, stat.as<QlStatus>());
+                                    sw.as<Sweep>(), sweep_cap, stat.as<QlStatus>()); sc::launched();
   SC_LAUNCH_CHECK();
   QlStatus hs;
   std::vector<double> dh((size_t)n);
@@ -357,11 +357,11 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
 
   if (n_vectors > 0) {
     SC_CUDA(Zt.alloc(sizeof(double) * nn, st));
-    k_identity<<<(unsigned)n, 256, 0, st>>>(Zt.as<double>(), n);
+    k_identity<<<(unsigned)n, 256, 0, st>>>(Zt.as<double>(), n); sc::launched();
     SC_LAUNCH_CHECK();
     if (hs.n_sweeps > 0) {
       k_apply_rotations<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(
-          Zt.as<double>(), n, sw.as<Sweep>(), hs.n_sweeps, rc.as<double>(), rs.as<double>());
+          Zt.as<double>(), n, sw.as<Sweep>(), hs.n_sweeps, rc.as<double>(), rs.as<double>()); sc::launched();
       SC_LAUNCH_CHECK();
     }
     SC_CUDA(selbuf.alloc(sizeof(int) * (size_t)n_vectors, st));
@@ -373,7 +373,7 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
                                  (int)smem));
     k_backtransform<<<(unsigned)n_vectors, 256, smem, st>>>(T.as<double>(), n, tau,
                                                             Zt.as<double>(), selbuf.as<int>(),
-                                                            n_vectors, left, right, v_dev);
+                                                            n_vectors, left, right, v_dev); sc::launched();
     SC_LAUNCH_CHECK();
     SC_CUDA(cudaStreamSynchronize(st));   // `order` must outlive the H2D copy
   }

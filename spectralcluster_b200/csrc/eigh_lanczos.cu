@@ -253,12 +253,12 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   auto Tat = [&](int i, int j) -> double& { return T[(size_t)i * (m + 1) + j]; };
 
   // start vector
-  k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull);
-  k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev);
+  k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull); sc::launched();
+  k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
   double nrm2 = 0.0;
   SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
   SC_CUDA(cudaStreamSynchronize(st));
-  k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V);
+  k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V); sc::launched();
   SC_LAUNCH_CHECK();
 
   int j = 0;                 // basis vectors V[0..j] valid, T[0..j-1][0..j-1] valid
@@ -270,17 +270,17 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   for (;;) {
     for (int i = j; i < m; ++i) {
       // w = flip * Op V_i
-      k_prescale<<<gn, 256, 0, st>>>(V + (size_t)i * n, left, right, n, t);
+      k_prescale<<<gn, 256, 0, st>>>(V + (size_t)i * n, left, right, n, t); sc::launched();
       k_symv_f32_f64<<<(unsigned)((n + SYMV_ROWS - 1) / SYMV_ROWS), SYMV_ROWS * 32, 0, st>>>(
-          s, n, lds, t, y);
-      k_postscale<<<gn, 256, 0, st>>>(V + (size_t)i * n, y, delta, left, right, sign, flip, n, w);
+          s, n, lds, t, y); sc::launched();
+      k_postscale<<<gn, 256, 0, st>>>(V + (size_t)i * n, y, delta, left, right, sign, flip, n, w); sc::launched();
       ++matvecs;
       // classical Gram-Schmidt twice against V_0..V_i
-      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev);
-      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w);
-      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h2_dev);
-      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h2_dev, w);
-      k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev);
+      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev); sc::launched();
+      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w); sc::launched();
+      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h2_dev); sc::launched();
+      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h2_dev, w); sc::launched();
+      k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
       SC_LAUNCH_CHECK();
       SC_CUDA(cudaMemcpyAsync(hh.data(), h_dev, sizeof(double) * (i + 1), cudaMemcpyDeviceToHost, st));
       SC_CUDA(cudaMemcpyAsync(hh2.data(), h2_dev, sizeof(double) * (i + 1), cudaMemcpyDeviceToHost, st));
@@ -295,18 +295,18 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
       const double scale = std::fabs(Tat(i, i)) + 1e-300;
       if (!(beta > 1e-13 * scale)) {
         // invariant subspace: continue with a fresh direction orthogonal to the basis
-        k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull + 7919ull * reseed++);
+        k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull + 7919ull * reseed++); sc::launched();
         for (int pass = 0; pass < 2; ++pass) {
-          k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev);
-          k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w);
+          k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev); sc::launched();
+          k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w); sc::launched();
         }
-        k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev);
+        k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
         SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
         SC_CUDA(cudaStreamSynchronize(st));
-        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V + (size_t)(i + 1) * n);
+        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V + (size_t)(i + 1) * n); sc::launched();
         beta = 0.0;
       } else {
-        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / beta, V + (size_t)(i + 1) * n);
+        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / beta, V + (size_t)(i + 1) * n); sc::launched();
       }
       Tat(i + 1, i) = beta;
       Tat(i, i + 1) = beta;
@@ -344,7 +344,7 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
       for (int p = 0; p < keep; ++p) zk[(size_t)q * 64 + p] = Z[(size_t)q * m + p];
     SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)m * 64,
                             cudaMemcpyHostToDevice, st));
-    k_combine<<<dim3(gn, (unsigned)((keep + 7) / 8)), 256, 0, st>>>(V, n, m, z_dev, 64, keep, V2);
+    k_combine<<<dim3(gn, (unsigned)((keep + 7) / 8)), 256, 0, st>>>(V, n, m, z_dev, 64, keep, V2); sc::launched();
     SC_CUDA(cudaMemcpyAsync(V2 + (size_t)keep * n, V + (size_t)m * n, sizeof(double) * (size_t)n,
                             cudaMemcpyDeviceToDevice, st));
     SC_CUDA(cudaStreamSynchronize(st));      // zk lives on the host stack frame
@@ -367,8 +367,8 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
     SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)m * 64,
                             cudaMemcpyHostToDevice, st));
     k_combine<<<dim3(gn, (unsigned)((n_vectors + 7) / 8)), 256, 0, st>>>(V, n, m, z_dev, 64,
-                                                                        (int)n_vectors, V2);
-    k_mapback<<<(unsigned)n_vectors, 512, 0, st>>>(V2, n, (int)n_vectors, left, right, v_dev);
+                                                                        (int)n_vectors, V2); sc::launched();
+    k_mapback<<<(unsigned)n_vectors, 512, 0, st>>>(V2, n, (int)n_vectors, left, right, v_dev); sc::launched();
     SC_LAUNCH_CHECK();
     SC_CUDA(cudaStreamSynchronize(st));
   }

@@ -88,6 +88,7 @@ int gemm_nt_simt(int epi, const float* A, int64_t lda, const float* B, int64_t l
                                                        rowmax_offdiag);
   else
     k_gemm_nt_simt<EPI_PLAIN><<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, C, ldc, nullptr);
+  sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -374,7 +374,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  kern<<<grid, NUM_THREADS, smem, st>>>(ah, al, bh, bl, M, N, K, C, ldc, rowmax);
+  kern<<<grid, NUM_THREADS, smem, st>>>(ah, al, bh, bl, M, N, K, C, ldc, rowmax); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -340,7 +340,7 @@ using namespace sc;
 
 extern "C" int sc_row_renorm(sc_context* ctx, double* e, int64_t n, int64_t k, void* stream) {
   SC_REQUIRE(ctx && e && n > 0 && k > 0, "sc_row_renorm: bad arguments");
-  k_row_renorm<<<(unsigned)((n + KT - 1) / KT), KT, 0, as_stream(stream)>>>(e, n, k);
+  k_row_renorm<<<(unsigned)((n + KT - 1) / KT), KT, 0, as_stream(stream)>>>(e, n, k); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -385,29 +385,29 @@ extern "C" int sc_kmeans(sc_context* ctx, const double* e, int64_t n, int64_t k_
   SC_CUDA(sbuf.alloc(sizeof(KmState), st));
   KmState* state = sbuf.as<KmState>();
 
-  k_state_init<<<1, 1, 0, st>>>(state);
+  k_state_init<<<1, 1, 0, st>>>(state); sc::launched();
   if (k > 1)
     SC_CUDA(cudaMemcpyAsync(u_dev, u_host, sizeof(double) * (size_t)(k - 1) * trials,
                             cudaMemcpyHostToDevice, st));
   // ---- stage 1: scikit-learn seeding + one Lloyd iteration
-  k_col_mean<<<(unsigned)k_dim, KT, 0, st>>>(e, n, k_dim, mean);
-  k_center<<<nb, KT, 0, st>>>(e, n, k_dim, mean, x, xsq);
-  k_kpp_first<<<nb, KT, 0, st>>>(x, xsq, n, k_dim, first_center, closest, part, centers);
-  k_kpp_reduce_pot<<<1, KT, 0, st>>>(part, nb, state);
+  k_col_mean<<<(unsigned)k_dim, KT, 0, st>>>(e, n, k_dim, mean); sc::launched();
+  k_center<<<nb, KT, 0, st>>>(e, n, k_dim, mean, x, xsq); sc::launched();
+  k_kpp_first<<<nb, KT, 0, st>>>(x, xsq, n, k_dim, first_center, closest, part, centers); sc::launched();
+  k_kpp_reduce_pot<<<1, KT, 0, st>>>(part, nb, state); sc::launched();
   SC_LAUNCH_CHECK();
   for (int64_t c = 1; c < k; ++c) {
     k_kpp_candidates<<<1, 1024, 0, st>>>(closest, n, u_dev + (c - 1) * trials, (int)trials, state,
-                                         cand);
-    k_kpp_trials<<<nb, KT, 0, st>>>(x, xsq, n, k_dim, closest, cand, (int)trials, newd, part);
-    k_kpp_choose<<<1, KT, 0, st>>>(part, nb, (int)trials, cand, x, k_dim, (int)c, centers, state);
-    k_kpp_commit<<<nb, KT, 0, st>>>(newd, n, state, closest);
+                                         cand); sc::launched();
+    k_kpp_trials<<<nb, KT, 0, st>>>(x, xsq, n, k_dim, closest, cand, (int)trials, newd, part); sc::launched();
+    k_kpp_choose<<<1, KT, 0, st>>>(part, nb, (int)trials, cand, x, k_dim, (int)c, centers, state); sc::launched();
+    k_kpp_commit<<<nb, KT, 0, st>>>(newd, n, state, closest); sc::launched();
   }
   SC_LAUNCH_CHECK();
-  k_assign<<<nb, KT, 0, st>>>(x, n, k_dim, centers, k, -1, labels, part, state);
+  k_assign<<<nb, KT, 0, st>>>(x, n, k_dim, centers, k, -1, labels, part, state); sc::launched();
   k_cluster_sums<<<dim3((unsigned)k, (unsigned)k_dim), KT, 0, st>>>(x, n, k_dim, labels, sums,
-                                                                    counts, counts_nz, state);
+                                                                    counts, counts_nz, state); sc::launched();
   k_lloyd_update<<<(unsigned)((k * k_dim + KT - 1) / KT), KT, 0, st>>>(sums, counts, k, k_dim,
-                                                                       mean, centers, state);
+                                                                       mean, centers, state); sc::launched();
   SC_LAUNCH_CHECK();
 
   // ---- stage 2: CustomKMeans.predict on the un-centred embeddings
@@ -416,11 +416,11 @@ extern "C" int sc_kmeans(sc_context* ctx, const double* e, int64_t n, int64_t k_
   for (;;) {
     const int batch = 4;
     for (int b = 0; b < batch; ++b) {
-      k_assign<<<nb, KT, 0, st>>>(e, n, k_dim, centers, k, metric, labels, part, state);
+      k_assign<<<nb, KT, 0, st>>>(e, n, k_dim, centers, k, metric, labels, part, state); sc::launched();
       k_cluster_sums<<<dim3((unsigned)k, (unsigned)k_dim), KT, 0, st>>>(e, n, k_dim, labels, sums,
-                                                                        counts, counts_nz, state);
+                                                                        counts, counts_nz, state); sc::launched();
       k_custom_step<<<1, KT, 0, st>>>(part, nb, n, sums, counts_nz, k, k_dim, tol, max_iter,
-                                      centers, counts, state);
+                                      centers, counts, state); sc::launched();
     }
     launched += batch;
     SC_LAUNCH_CHECK();

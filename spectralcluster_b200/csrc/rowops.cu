@@ -268,6 +268,7 @@ extern "C" int sc_normalize_rows(sc_context* ctx, const void* x, int x_is_f64, i
   else
     k_normalize_rows<float><<<grid, warps * 32, 0, as_stream(stream)>>>(
         (const float*)x, n, d, ldx, xn, ldxn, (__half*)hi, (__half*)lo, ldh);
+  sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -275,7 +276,7 @@ extern "C" int sc_normalize_rows(sc_context* ctx, const void* x, int x_is_f64, i
 extern "C" int sc_crop_diagonal(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                                 float* out, int64_t ldo, void* stream) {
   SC_REQUIRE(ctx && a && out && n > 0, "sc_crop_diagonal: bad arguments");
-  k_crop_diagonal<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, out, ldo, nullptr);
+  k_crop_diagonal<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, out, ldo, nullptr); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -283,7 +284,7 @@ extern "C" int sc_crop_diagonal(sc_context* ctx, const float* a, int64_t n, int6
 extern "C" int sc_crop_diagonal_values(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                                        float* diag_out, void* stream) {
   SC_REQUIRE(ctx && a && diag_out && n > 0, "sc_crop_diagonal_values: bad arguments");
-  k_crop_diagonal<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, nullptr, 0, diag_out);
+  k_crop_diagonal<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, nullptr, 0, diag_out); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -296,7 +297,7 @@ extern "C" int sc_row_threshold(sc_context* ctx, const float* a, int64_t n, int6
              "Unsupported thresholding_type");
   const double q = (p * 100.0) / 100.0;   // the reference passes p*100 to np.percentile
   k_row_threshold<<<(unsigned)n, 256, 0, as_stream(stream)>>>(
-      a, n, lda, type, (float)p, q, (float)mult, binarize, preserve_diagonal, out, ldo);
+      a, n, lda, type, (float)p, q, (float)mult, binarize, preserve_diagonal, out, ldo); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -307,7 +308,7 @@ extern "C" int sc_symmetrize(sc_context* ctx, const float* a, int64_t n, int64_t
   SC_REQUIRE(type == SC_SYMMETRIZE_MAX || type == SC_SYMMETRIZE_AVERAGE,
              "Unsupported symmetrize_type.");
   const unsigned t = (unsigned)((n + 31) / 32);
-  k_symmetrize<<<dim3(t, t), dim3(32, 8), 0, as_stream(stream)>>>(a, n, lda, type, out, ldo);
+  k_symmetrize<<<dim3(t, t), dim3(32, 8), 0, as_stream(stream)>>>(a, n, lda, type, out, ldo); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -317,7 +318,7 @@ extern "C" int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64
   SC_REQUIRE(ctx && a && hi && lo && n > 0, "sc_split_planes: bad arguments");
   const unsigned gx = (unsigned)((n + 1023) / 1024);
   k_split_planes<<<dim3((unsigned)n, gx), 256, 0, as_stream(stream)>>>(a, n, lda, (__half*)hi,
-                                                                        (__half*)lo, ldh);
+                                                                        (__half*)lo, ldh); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -325,7 +326,7 @@ extern "C" int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64
 extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                             double* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && a && n > 0, "sc_row_stats: bad arguments");
-  k_row_stats<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, rowmax, rowsum);
+  k_row_stats<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, rowmax, rowsum); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -333,7 +334,7 @@ extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t 
 extern "C" int sc_row_normalize(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                                 float* out, int64_t ldo, void* stream) {
   SC_REQUIRE(ctx && a && out && n > 0, "sc_row_normalize: bad arguments");
-  k_row_normalize<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, out, ldo);
+  k_row_normalize<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, out, ldo); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -346,11 +347,11 @@ extern "C" int sc_laplacian(sc_context* ctx, const float* w, int64_t n, int64_t 
   cudaStream_t st = as_stream(stream);
   Scratch deg;
   SC_CUDA(deg.alloc(sizeof(double) * (size_t)n, st));
-  k_row_stats<<<(unsigned)n, 256, 0, st>>>(w, n, ldw, nullptr, deg.as<double>());
+  k_row_stats<<<(unsigned)n, 256, 0, st>>>(w, n, ldw, nullptr, deg.as<double>()); sc::launched();
   SC_LAUNCH_CHECK();
   const unsigned gx = (unsigned)((n + 255) / 256);
   k_laplacian<<<dim3((unsigned)n, gx), 256, 0, st>>>(w, n, ldw, type, eps, deg.as<double>(), out,
-                                                     ldo);
+                                                     ldo); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import time
 import typing
 
@@ -59,8 +60,7 @@ class Engine:
     self.device = t.device("cuda", device)
     self.ctx = nat.context(device)
     self.gemm_precision = nat.GEMM_SPLIT3
-    self.timings: typing.Dict[str, float] = {}
-    self.launches = 0
+    self.profile = None
 
   @classmethod
   def get(cls, device: typing.Optional[int] = None) -> "Engine":
@@ -105,11 +105,33 @@ class Engine:
     return m[:, :n].to("cpu").numpy().astype(np.float64)
 
   def call(self, name, *args, exc=nat.NativeError):
-    self.launches += 1
+    """One C-ABI call on the current stream; with `profile` on, bracketed by CUDA events."""
+    if self.profile is None:
+      nat.call(name, self.ctx, *args, exc=exc)
+      return
+    t = torch()
+    start, stop = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    start.record()
     nat.call(name, self.ctx, *args, exc=exc)
+    stop.record()
+    self.profile.append((name, start, stop))
+
+  def start_profile(self):
+    self.profile = []
+
+  def stop_profile(self) -> typing.Dict[str, float]:
+    """Milliseconds per C-ABI entry point since start_profile() (device time, CUDA events)."""
+    torch().cuda.synchronize(self.device)
+    out: typing.Dict[str, float] = {}
+    for name, start, stop in self.profile or []:
+      out[name] = out.get(name, 0.0) + start.elapsed_time(stop)
+    self.profile = None
+    return out
 
   # ---- operators (device in / device out)
   def gemm_engine(self, n: int) -> int:
+    if os.environ.get("SCB_FORCE_SIMT") == "1":    # debugging aid: validation GEMM everywhere
+      return nat.GEMM_SIMT
     return nat.GEMM_SIMT if n < self.simt_below else nat.GEMM_TCGEN05
 
   def affinity(self, x_dev, want_crop_vector: bool):

@@ -19,7 +19,7 @@ def declared_functions():
   text = open(HEADER).read()
   text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
   out = {}
-  for m in re.finditer(r"\b(?:int|const char\*)\s+(sc_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+  for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(sc_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
     args = m.group(2).strip()
     out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
   return out
