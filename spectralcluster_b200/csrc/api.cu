@@ -27,7 +27,7 @@ int gemm_nt_simt(int epi, const float* A, int64_t lda, const float* B, int64_t l
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, cudaStream_t st);
+                    float* rowmax_offdiag, bool symmetric, cudaStream_t st);
 
 }  // namespace sc
 
@@ -93,7 +93,7 @@ extern "C" int sc_affinity_cosine(sc_context* ctx, int engine, int precision, co
              "sc_affinity_cosine: the tcgen05 engine needs the split fp16 planes");
   return gemm_nt_tcgen05(ctx, 1, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, d, a, lda,
-                         rowmax_offdiag, as_stream(stream));
+                         rowmax_offdiag, /*symmetric=*/false, as_stream(stream));
 }
 
 extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y,
@@ -109,5 +109,5 @@ extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const floa
              "sc_diffuse: the tcgen05 engine needs the split fp16 planes");
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, n, s, lds, nullptr,
-                         as_stream(stream));
+                         /*symmetric=*/true, as_stream(stream));
 }

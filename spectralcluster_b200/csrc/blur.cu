@@ -138,18 +138,13 @@ k_blur_generic(const BlurArgs g, const BlurWeights bw) {
 constexpr int TTH = 32, TTW = 128, TTHREADS = 256, STRIP = 8;
 
 template <int R, int EPI>
-__global__ void __launch_bounds__(TTHREADS)
-k_blur_tile(const BlurArgs g, const BlurWeights bw) {
+__device__ __forceinline__ void blur_tile_body(const BlurArgs& g, const float (&w)[2 * R + 1],
+                                               int64_t row0, int64_t col0, float* smem,
+                                               int* band_max) {
   constexpr int IW = TTW + 2 * R, IH = TTH + 2 * R;
   constexpr int MP = TTH + 1;                         // transposed pitch
-  extern __shared__ float smem[];
-  float* in = smem;                                    // [IH][IW]; reused as out [TTH][TTW]
+  float* in = smem;                                    // [IH][IW]; reused as out [TTH][TTW+1]
   float* midT = smem + IH * IW;                        // [IW][MP]
-  const int64_t row0 = (int64_t)blockIdx.y * TTH, col0 = (int64_t)blockIdx.x * TTW;
-  float w[2 * R + 1];
-#pragma unroll
-  for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
-
   const bool interior = (row0 >= R) && (col0 >= R) && (row0 + TTH + R <= g.n) &&
                         (col0 + TTW + R <= g.n);
   for (int idx = threadIdx.x; idx < IH * IW; idx += TTHREADS) {
@@ -177,25 +172,21 @@ k_blur_tile(const BlurArgs g, const BlurWeights bw) {
     }
   }
   __syncthreads();
-  // horizontal: items = TTH rows x (TTW/STRIP) strips; lanes run along rows
-  float* outs = in;                                    // [TTH][TTW]  (input tile is dead now)
+  // horizontal: items = TTH rows x (TTW/STRIP) strips; lanes run along rows.  All reads of
+  // `in` finished before the barrier above, so it can take the outputs.
+  float* outs = in;
   for (int item = threadIdx.x; item < TTH * (TTW / STRIP); item += TTHREADS) {
     const int r = item % TTH, c0 = (item / TTH) * STRIP;
     float win[STRIP + 2 * R];
 #pragma unroll
     for (int k = 0; k < STRIP + 2 * R; ++k) win[k] = midT[(c0 + k) * MP + r];
-    float res[STRIP];
 #pragma unroll
     for (int o = 0; o < STRIP; ++o) {
       float acc = 0.0f;
 #pragma unroll
       for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
-      res[o] = acc;
+      outs[r * (TTW + 1) + c0 + o] = acc;
     }
-    // all vertical reads of `in` finished before the barrier above; the horizontal pass reads
-    // midT only, so overwriting `in` here is safe.
-#pragma unroll
-    for (int o = 0; o < STRIP; ++o) outs[r * (TTW + 1) + c0 + o] = res[o];
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < TTH * TTW; idx += TTHREADS) {
@@ -203,12 +194,49 @@ k_blur_tile(const BlurArgs g, const BlurWeights bw) {
     const int64_t i = row0 + r, j = col0 + c;
     float v = 0.0f;
     if (i < g.n && j < g.n) v = blur_epilogue<EPI>(g, i, j, outs[r * (TTW + 1) + c]);
-    if (EPI != EPI_THRSYM && g.rowmax_out) {
-      v = fmaxf(v, 0.0f);
-      v = warp_max(v);
-      if ((threadIdx.x & 31) == 0 && i < g.n) atomic_max_nonneg(g.rowmax_out + i, v);
+    if (EPI != EPI_THRSYM && (band_max || g.rowmax_out)) {
+      v = warp_max(fmaxf(v, 0.0f));
+      if ((threadIdx.x & 31) == 0 && i < g.n) {
+        if (band_max) atomicMax(band_max + r, __float_as_int(v));     // shared, non-negative
+        else atomic_max_nonneg(g.rowmax_out + i, v);
+      }
     }
   }
+}
+
+// one tile per CTA (EPI_STORE / EPI_THRSYM)
+template <int R, int EPI>
+__global__ void __launch_bounds__(TTHREADS)
+k_blur_tile(const BlurArgs g, const BlurWeights bw) {
+  extern __shared__ float smem[];
+  float w[2 * R + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
+  blur_tile_body<R, EPI>(g, w, (int64_t)blockIdx.y * TTH, (int64_t)blockIdx.x * TTW, smem,
+                         nullptr);
+}
+
+// statistics pass: one CTA per 32-row band sweeps all column tiles and keeps the 32 running row
+// maxima in shared memory -- no global atomics (the 2-D version issued N^2/32 of them onto N
+// addresses and ran at 4% of the HBM roofline).
+template <int R>
+__global__ void __launch_bounds__(TTHREADS)
+k_blur_band_stats(const BlurArgs g, const BlurWeights bw) {
+  extern __shared__ float smem[];
+  __shared__ int band_max[TTH];
+  float w[2 * R + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
+  if (threadIdx.x < TTH) band_max[threadIdx.x] = 0;    // bit pattern of +0.0f
+  const int64_t row0 = (int64_t)blockIdx.x * TTH;
+  const int ntx = (int)((g.n + TTW - 1) / TTW);
+  for (int tx = 0; tx < ntx; ++tx) {
+    __syncthreads();                                   // previous tile's readers are done
+    blur_tile_body<R, EPI_STATS>(g, w, row0, (int64_t)tx * TTW, smem, band_max);
+  }
+  __syncthreads();
+  if (threadIdx.x < TTH && row0 + threadIdx.x < g.n)
+    g.rowmax_out[row0 + threadIdx.x] = __int_as_float(band_max[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ no blur (sigma == 0)
@@ -263,6 +291,14 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
     constexpr int R = 4;
     const size_t smem = sizeof(float) * ((TTH + 2 * R) * (TTW + 2 * R) + (TTW + 2 * R) * (TTH + 1));
     static_assert((TTH + 2 * R) * (TTW + 2 * R) >= TTH * (TTW + 1), "output staging must fit");
+    if (EPI == EPI_STATS) {
+      auto kband = k_blur_band_stats<R>;
+      SC_CUDA(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kband<<<(unsigned)((g.n + TTH - 1) / TTH), TTHREADS, smem, st>>>(g, bw);
+      sc::launched();
+      SC_LAUNCH_CHECK();
+      return 0;
+    }
     auto kern = k_blur_tile<R, EPI>;
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 grid((unsigned)((g.n + TTW - 1) / TTW), (unsigned)((g.n + TTH - 1) / TTH));

@@ -264,10 +264,41 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   int j = 0;                 // basis vectors V[0..j] valid, T[0..j-1][0..j-1] valid
   int64_t matvecs = 0, restarts = 0;
   int converged = 0;
+  int mm = m;                // size of the projected problem behind theta / Z
   std::vector<double> theta, Z;
   double beta_last = 0.0;
   uint64_t reseed = 1;
-  for (;;) {
+
+  // Rayleigh-Ritz on the leading sz x sz block of T; Ritz values sorted descending.  Returns how
+  // many of the first nev pairs have residual |beta * Z[sz-1, p]| <= tol * max|theta|.
+  auto ritz = [&](int sz, double beta) -> int {
+    std::vector<double> A((size_t)sz * sz);
+    for (int r = 0; r < sz; ++r)
+      for (int c = 0; c < sz; ++c) A[(size_t)r * sz + c] = 0.5 * (Tat(r, c) + Tat(c, r));
+    std::vector<double> wv, zv;
+    jacobi_eigh(A, sz, wv, zv);
+    std::vector<int> ord(sz);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return wv[a] > wv[b]; });
+    theta.assign(sz, 0.0);
+    Z.assign((size_t)sz * sz, 0.0);
+    for (int p = 0; p < sz; ++p) {
+      theta[p] = wv[ord[p]];
+      for (int q = 0; q < sz; ++q) Z[(size_t)q * sz + p] = zv[(size_t)q * sz + ord[p]];
+    }
+    mm = sz;
+    double tmax = 0.0;
+    for (int p = 0; p < sz; ++p) tmax = std::max(tmax, std::fabs(theta[p]));
+    int ok = 0;
+    for (int p = 0; p < nev && p < sz; ++p) {
+      if (std::fabs(beta * Z[(size_t)(sz - 1) * sz + p]) <= tol * tmax) ++ok;
+      else break;
+    }
+    return ok;
+  };
+
+  bool done = false;
+  while (!done) {
     for (int i = j; i < m; ++i) {
       // w = flip * Op V_i
       k_prescale<<<gn, 256, 0, st>>>(V + (size_t)i * n, left, right, n, t); sc::launched();
@@ -311,30 +342,15 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
       Tat(i + 1, i) = beta;
       Tat(i, i + 1) = beta;
       beta_last = beta;
+      // early exit: test the Ritz pairs of the growing basis every 8 steps
+      const int sz = i + 1;
+      if (sz < m && sz >= 2 * nev && sz % 8 == 0) {
+        converged = ritz(sz, beta);
+        if (converged >= nev) { done = true; break; }
+      }
     }
-    // Rayleigh-Ritz on the leading m x m block
-    std::vector<double> A((size_t)m * m);
-    for (int r = 0; r < m; ++r)
-      for (int c = 0; c < m; ++c) A[(size_t)r * m + c] = 0.5 * (Tat(r, c) + Tat(c, r));
-    std::vector<double> wv, zv;
-    jacobi_eigh(A, m, wv, zv);
-    std::vector<int> ord(m);
-    std::iota(ord.begin(), ord.end(), 0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return wv[a] > wv[b]; });
-    theta.assign(m, 0.0);
-    Z.assign((size_t)m * m, 0.0);
-    for (int p = 0; p < m; ++p) {
-      theta[p] = wv[ord[p]];
-      for (int q = 0; q < m; ++q) Z[(size_t)q * m + p] = zv[(size_t)q * m + ord[p]];
-    }
-    double tmax = 0.0;
-    for (int p = 0; p < m; ++p) tmax = std::max(tmax, std::fabs(theta[p]));
-    converged = 0;
-    for (int p = 0; p < nev; ++p) {
-      const double resid = std::fabs(beta_last * Z[(size_t)(m - 1) * m + p]);
-      if (resid <= tol * tmax) ++converged;
-      else break;
-    }
+    if (done) break;
+    converged = ritz(m, beta_last);
     if (converged >= nev || matvecs >= max_matvecs) break;
     // thick restart: keep the leading `keep` Ritz vectors (all converged + a buffer)
     int keep = std::min(m - 8, nev + keep_extra);
@@ -361,12 +377,12 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   }
   for (int p = 0; p < nev; ++p) w_host[p] = flip * theta[p];
   if (n_vectors > 0) {
-    std::vector<double> zk((size_t)m * 64, 0.0);
-    for (int q = 0; q < m; ++q)
-      for (int p = 0; p < (int)n_vectors; ++p) zk[(size_t)q * 64 + p] = Z[(size_t)q * m + p];
-    SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)m * 64,
+    std::vector<double> zk((size_t)mm * 64, 0.0);
+    for (int q = 0; q < mm; ++q)
+      for (int p = 0; p < (int)n_vectors; ++p) zk[(size_t)q * 64 + p] = Z[(size_t)q * mm + p];
+    SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)mm * 64,
                             cudaMemcpyHostToDevice, st));
-    k_combine<<<dim3(gn, (unsigned)((n_vectors + 7) / 8)), 256, 0, st>>>(V, n, m, z_dev, 64,
+    k_combine<<<dim3(gn, (unsigned)((n_vectors + 7) / 8)), 256, 0, st>>>(V, n, mm, z_dev, 64,
                                                                         (int)n_vectors, V2); sc::launched();
     k_mapback<<<(unsigned)n_vectors, 512, 0, st>>>(V2, n, (int)n_vectors, left, right, v_dev); sc::launched();
     SC_LAUNCH_CHECK();

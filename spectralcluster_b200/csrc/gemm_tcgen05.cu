@@ -134,42 +134,93 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 struct TileCoord {
   int m_blk, n_blk;
 };
-__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles_n) {
-  const int group = GROUP_M * tiles_n;
-  const int g = tile / group;
-  const int first_m = g * GROUP_M;
-  const int gm = min(GROUP_M, tiles_m - first_m);
-  const int r = tile - g * group;
+
+// Rasterisation.  Full problem: groups of GROUP_M M-blocks sweep all N-blocks.  Symmetric
+// problem (C = Y Y^T): only tiles that touch the upper triangle are computed, i.e.
+// 128 m_blk < 256 (n_blk + 1); the rest is filled by mirrored stores.  group_start[g] is the
+// first tile index of group g (host-computed with the same counting rule).
+constexpr int MAX_GROUPS = 160;
+struct TileTable {
+  int group_start[MAX_GROUPS + 1];
+  int num_groups;
+  int num_tiles;
+};
+
+__host__ __device__ inline int sym_valid_mblocks(int g, int n_blk, int tiles_m) {
+  // m blocks of group g that are valid for column block n_blk: m_blk <= 2 n_blk + 1
+  int lim = 2 * n_blk + 2 - g * GROUP_M;
+  const int avail = tiles_m - g * GROUP_M;
+  if (lim > GROUP_M) lim = GROUP_M;
+  if (lim > avail) lim = avail;
+  return lim < 0 ? 0 : lim;
+}
+
+template <bool SYM>
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles_n,
+                                                const TileTable& tab) {
   TileCoord t;
-  t.m_blk = first_m + r % gm;
-  t.n_blk = r / gm;
+  if (!SYM) {
+    const int group = GROUP_M * tiles_n;
+    const int g = tile / group;
+    const int first_m = g * GROUP_M;
+    const int gm = min(GROUP_M, tiles_m - first_m);
+    const int r = tile - g * group;
+    t.m_blk = first_m + r % gm;
+    t.n_blk = r / gm;
+  } else {
+    int g = 0;
+    while (g + 1 < tab.num_groups && tab.group_start[g + 1] <= tile) ++g;
+    int r = tile - tab.group_start[g];
+    int nb = (g * GROUP_M) / 2;            // first column block that touches the group
+    for (;; ++nb) {
+      const int cnt = sym_valid_mblocks(g, nb, tiles_m);
+      if (r < cnt) break;
+      r -= cnt;
+    }
+    t.m_blk = g * GROUP_M + r;
+    t.n_blk = nb;
+  }
   return t;
 }
 
-template <bool SPLIT, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS_V2 = 128 + NUM_EPI_WARPS * 32;   // 384
+
+// C = A B^T with the accumulation split in two levels:
+//   level 1 (tensor core, TMEM): a chain of only CHUNK_KB K-blocks (24 or 16 MMAs).  tcgen05
+//           accumulates in fp32 with truncation, which biases long chains low by ~5e-8 per MMA
+//           (measured: -1.5e-5 relative at K = 1536); short chains keep that below 1e-6.
+//   level 2 (CUDA cores, registers): the epilogue warps pull each finished chain out of TMEM
+//           (tcgen05.ld) and add it, round-to-nearest, into a register-resident 128 x 256 fp32
+//           tile (8 warps x 32 lanes x 128 registers), while the tensor core is already working
+//           on the next chain in the other TMEM buffer.
+template <bool SPLIT, int EPI, bool SYM>
+__global__ void __launch_bounds__(NUM_THREADS_V2, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi,
-               const __grid_constant__ CUtensorMap map_b_lo, int M, int N, int K,
+               const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ TileTable tab, int M, int N, int K,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag) {
   constexpr int STAGES = SPLIT ? 2 : 4;
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
+  // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
+  constexpr int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? 1 : (SPLIT ? 2 : 4);
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = SYM ? tab.num_tiles : tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -186,7 +237,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);      // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -202,116 +253,150 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(tile, tiles_m, tiles_n);
-        const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-          mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
-          const int k0 = kb * BK;
-          tma_load_2d(base, &map_a_hi, bar, k0, row_a);
-          tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
-          if (SPLIT) {
-            tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
-            tma_load_2d(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_b_lo, bar, k0, row_b);
+  if (warp < 4) {
+    // producer / MMA warpgroup gives its registers to the epilogue warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================================================== TMA producer
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const TileCoord tc = tile_coord<SYM>(tile, tiles_m, tiles_n, tab);
+          const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t bar = smem_u32(&full_bar[stage]);
+            const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+            mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
+            const int k0 = kb * BK;
+            tma_load_2d(base, &map_a_hi, bar, k0, row_a);
+            tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
+            if (SPLIT) {
+              tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
+              tma_load_2d(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_b_lo, bar, k0, row_b);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);   // epilogue drained this buffer
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tcgen05_fence_after();
-          const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(base);
-          const uint64_t b_hi = make_smem_desc(base + A_PLANE_BYTES);
-          const uint64_t a_lo = make_smem_desc(base + A_PLANE_BYTES + B_PLANE_BYTES);
-          const uint64_t b_lo = make_smem_desc(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the >>4 address
-            const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
-            umma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | kk) ? 1u : 0u);
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int in_chunk = kb % CHUNK_KB;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            if (in_chunk == 0) {
+              mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);   // chain buffer drained
+              tcgen05_fence_after();
+            }
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tcgen05_fence_after();
+            const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t a_hi = make_smem_desc(base);
+            const uint64_t b_hi = make_smem_desc(base + A_PLANE_BYTES);
+            const uint64_t a_lo = make_smem_desc(base + A_PLANE_BYTES + B_PLANE_BYTES);
+            const uint64_t b_lo = make_smem_desc(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+            // The small cross products go first: tcgen05 truncates each accumulate to the
+            // accumulator's current ulp, so terms added while the chain is still small cost
+            // almost nothing; only the BK/16 hi*hi accumulates run at full magnitude.
             if (SPLIT) {
-              umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
+                umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, (in_chunk | kk) ? 1u : 0u);
+                umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
+              umma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, (SPLIT || in_chunk || kk) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (in_chunk == CHUNK_KB - 1 || kb == num_kb - 1) {
+              umma_commit(smem_u32(&tfull_bar[acc]));            // chain complete
+              if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));      // stage reusable when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));          // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================================================== epilogue (TMEM -> regs -> global)
+  } else {
+    // ===================================================== epilogue warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int quad = warp & 3;                            // TMEM lanes 32*quad .. +31
+    const int half = (warp - 4) >> 2;                     // columns [128*half, +128)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(tile, tiles_m, tiles_n);
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tcgen05_fence_after();
+      const TileCoord tc = tile_coord<SYM>(tile, tiles_m, tiles_n, tab);
+      float sum[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) sum[i] = 0.0f;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * 128) +
+                               ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] += __uint_as_float(v[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      // ---- write-out
       const int64_t row = (int64_t)tc.m_blk * BM + quad * 32 + lane;
-      const int64_t col0 = (int64_t)tc.n_blk * BN;
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16);
+      const int64_t col0 = (int64_t)tc.n_blk * BN + half * 128;
       float rmax = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        if (row < M) {
-          float* dst = C + row * ldc + col0 + c * 32;
+      if (EPI == TC_EPI_AFFINITY) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int64_t col = col0 + c * 32 + q * 4;
-            float f[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float x = __uint_as_float(v[q * 4 + t]);
-              if (EPI == TC_EPI_AFFINITY) {
-                x = (x + 1.0f) * 0.5f;                    // utils.py:39
-                if (col + t != row && col + t < N) rmax = fmaxf(rmax, x);
-              }
-              f[t] = x;
-            }
-            if (col + 3 < N) {
-              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(f[0], f[1], f[2], f[3]);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (col + t < N) dst[q * 4 + t] = f[t];
-            }
-          }
+        for (int i = 0; i < 128; ++i) {
+          sum[i] = (sum[i] + 1.0f) * 0.5f;                 // utils.py:39
+          if (col0 + i != row && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-      if (EPI == TC_EPI_AFFINITY && rowmax_offdiag && row < M)
-        atomic_max_nonneg(rowmax_offdiag + row, rmax);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (row < M) {
+        float* dst = C + row * ldc + col0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int64_t col = col0 + q * 4;
+          if (col + 3 < N) {
+            *reinterpret_cast<float4*>(dst + q * 4) =
+                make_float4(sum[q * 4], sum[q * 4 + 1], sum[q * 4 + 2], sum[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < N) dst[q * 4 + t] = sum[q * 4 + t];
+          }
+        }
+        if (EPI == TC_EPI_AFFINITY && rowmax_offdiag) atomic_max_nonneg(rowmax_offdiag + row, rmax);
+      }
+      if (SYM) {
+        // mirror into the tiles that were skipped: target (col, row) lies in tile
+        // (col/128, row/256), which is skipped iff col/128 >= 2 (row/256) + 2.  col0 is a
+        // multiple of 128, so the decision is uniform over this thread's 128 columns.
+        const bool mirror = (col0 / BM) >= 2 * (row / BN) + 2;
+        if (mirror && row < M) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (col0 + i < N) C[(col0 + i) * ldc + row] = sum[i];   // lanes -> consecutive rows
+        }
+      }
     }
   }
   tcgen05_fence_before();
@@ -362,7 +447,18 @@ static int make_plane_map(CUtensorMap* map, const __half* ptr, int64_t rows, int
   return 0;
 }
 
-template <bool SPLIT, int EPI>
+static void build_tile_table(TileTable& tab, int tiles_m, int tiles_n) {
+  tab.num_groups = (tiles_m + GROUP_M - 1) / GROUP_M;
+  int total = 0;
+  for (int g = 0; g < tab.num_groups; ++g) {
+    tab.group_start[g] = total;
+    for (int nb = (g * GROUP_M) / 2; nb < tiles_n; ++nb) total += sym_valid_mblocks(g, nb, tiles_m);
+  }
+  tab.group_start[tab.num_groups] = total;
+  tab.num_tiles = total;
+}
+
+template <bool SPLIT, int EPI, bool SYM>
 static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
                   const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
                   int64_t ldc, float* rowmax, cudaStream_t st) {
@@ -370,11 +466,19 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   SC_REQUIRE(smem <= ctx->smem_optin, "tcgen05 GEMM needs %zu B of shared memory", smem);
-  auto kern = k_gemm_tcgen05<SPLIT, EPI>;
+  auto kern = k_gemm_tcgen05<SPLIT, EPI, SYM>;
   SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  TileTable tab = {};
+  int tiles = tiles_m * tiles_n;
+  if (SYM) {
+    SC_REQUIRE((tiles_m + GROUP_M - 1) / GROUP_M <= MAX_GROUPS, "tcgen05 GEMM: N too large for "
+               "the symmetric tile table");
+    build_tile_table(tab, tiles_m, tiles_n);
+    tiles = tab.num_tiles;
+  }
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  kern<<<grid, NUM_THREADS, smem, st>>>(ah, al, bh, bl, M, N, K, C, ldc, rowmax); sc::launched();
+  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -382,7 +486,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, cudaStream_t st) {
+                    float* rowmax_offdiag, bool symmetric, cudaStream_t st) {
   SC_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31),
              "tcgen05 GEMM: bad shape");
   SC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0,
@@ -398,18 +502,20 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
     al = ah;
     bl = bh;
   }
+  const int m = (int)M, n = (int)N, k = (int)K;
+  // C = Y Y^T is symmetric when both operands are the same matrix: compute the upper tiles only
+  const bool sym = symmetric && a_hi == b_hi && a_lo == b_lo && M == N && lda == ldb;
+#define SC_TC_LAUNCH(SP, EP, SY) \
+  return launch<SP, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, st)
   if (split) {
-    if (epi == TC_EPI_AFFINITY)
-      return launch<true, TC_EPI_AFFINITY>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
-                                           rowmax_offdiag, st);
-    return launch<true, TC_EPI_PLAIN>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
-                                      nullptr, st);
+    if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(true, TC_EPI_AFFINITY, true); SC_TC_LAUNCH(true, TC_EPI_AFFINITY, false); }
+    if (sym) SC_TC_LAUNCH(true, TC_EPI_PLAIN, true);
+    SC_TC_LAUNCH(true, TC_EPI_PLAIN, false);
   }
-  if (epi == TC_EPI_AFFINITY)
-    return launch<false, TC_EPI_AFFINITY>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc,
-                                          rowmax_offdiag, st);
-  return launch<false, TC_EPI_PLAIN>(ctx, ah, al, bh, bl, (int)M, (int)N, (int)K, C, ldc, nullptr,
-                                     st);
+  if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(false, TC_EPI_AFFINITY, true); SC_TC_LAUNCH(false, TC_EPI_AFFINITY, false); }
+  if (sym) SC_TC_LAUNCH(false, TC_EPI_PLAIN, true);
+  SC_TC_LAUNCH(false, TC_EPI_PLAIN, false);
+#undef SC_TC_LAUNCH
 }
 
 }  // namespace sc

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Key metrics of every kernel in an .ncu-rep (ncu -i <rep> --page raw --csv), one block each.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "lts__t_bytes.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg",
+    "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+]
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                     text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+col = {h: i for i, h in enumerate(hdr)}
+print("# %s" % rep)
+for r in rows[2:]:
+  print("== %s" % r[col["Kernel Name"]][:110])
+  for k in KEYS:
+    hits = [h for h in hdr if h.endswith(k)]
+    for h in hits[:1]:
+      print("   %-82s %s %s" % (k, r[col[h]], units[col[h]]))
