@@ -143,6 +143,36 @@ int sc_row_normalize(sc_context* ctx, const float* a, int64_t n, int64_t lda, fl
 int sc_laplacian(sc_context* ctx, const float* w, int64_t n, int64_t ldw, int type, double eps,
                  float* out, int64_t ldo, void* stream);
 
+/* ---- row-block variants for the row-sharded multi-GPU pipeline ------------- */
+/* Rows [row_begin, row_begin+row_count) of the affinity (utils.py:35-39) from the split planes of
+ * ALL n normalised embeddings.  rowmax_offdiag_block is indexed by local row. */
+int sc_affinity_cosine_block(sc_context* ctx, int precision, const void* hi, const void* lo,
+                             int64_t ldh, int64_t n, int64_t d, int64_t row_begin,
+                             int64_t row_count, float* a_block, int64_t lda,
+                             float* rowmax_offdiag_block, void* stream);
+/* Blur statistics / blur+threshold+symmetrize for global rows [row_begin, row_end) when `a` holds
+ * global rows [in_row_base, in_row_base+in_rows) (owned rows + the blur halo, recomputed locally
+ * rather than exchanged).  Output buffers start at global row row_begin; diag_override, rowmax and
+ * rowmax_out are indexed by GLOBAL row.  (row_end-row_begin) % 32 == 0 unless row_end == n. */
+int sc_gaussian_blur_rowmax_block(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                                  int64_t in_row_base, int64_t in_rows, int64_t row_begin,
+                                  int64_t row_end, const float* diag_override, double sigma,
+                                  int zero_diagonal, float* rowmax_out, void* stream);
+int sc_blur_threshold_symmetrize_block(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                                       int64_t in_row_base, int64_t in_rows, int64_t row_begin,
+                                       int64_t row_end, const float* diag_override, double sigma,
+                                       const float* rowmax, double p, double mult, int binarize,
+                                       int preserve_diagonal, int sym_type, float* y, int64_t ldy,
+                                       void* hi, void* lo, int64_t ldh, void* stream);
+/* Row maxima / sums of a rectangular [rows, cols] block (local rows of a sharded matrix). */
+int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows, int64_t cols, int64_t lda,
+                       double* rowmax, double* rowsum, void* stream);
+/* c[m,n] = (a_hi+a_lo)[m,k] (b_hi+b_lo)[n,k]^T : one (row block) x (peer row block) piece of
+ * Diffuse (refinement.py:232-234) in the sharded pipeline. */
+int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi, const void* a_lo,
+                      int64_t lda, int64_t m, const void* b_hi, const void* b_lo, int64_t ldb,
+                      int64_t n, int64_t k, float* c, int64_t ldc, void* stream);
+
 /* ---- utils.compute_sorted_eigenvectors (utils.py:44-71) ------------------------------ */
 /* The matrix decomposed is M = diag(delta) + sign * diag(left) S diag(right) with S symmetric
  * fp32 and left,right > 0; delta/left/right are fp64 device vectors, NULL

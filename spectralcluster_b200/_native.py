@@ -47,6 +47,16 @@ PROTOTYPES = {
     "sc_row_stats": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "sc_row_normalize": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_laplacian": [c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr, c_i64, c_ptr],
+    "sc_affinity_cosine_block": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                 c_ptr, c_i64, c_ptr, c_ptr],
+    "sc_gaussian_blur_rowmax_block": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                      c_ptr, c_dbl, c_int, c_ptr, c_ptr],
+    "sc_blur_threshold_symmetrize_block": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                           c_ptr, c_dbl, c_ptr, c_dbl, c_dbl, c_int, c_int, c_int,
+                                           c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr],
+    "sc_row_stats_block": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "sc_gemm_nt_planes": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64,
+                          c_i64, c_ptr, c_i64, c_ptr],
     "sc_eigh_dense": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                       c_i64, c_ptr, c_ptr, c_ptr],
     "sc_eigh_extremal": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,

@@ -27,7 +27,7 @@ int gemm_nt_simt(int epi, const float* A, int64_t lda, const float* B, int64_t l
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, bool symmetric, cudaStream_t st);
+                    float* rowmax_offdiag, bool symmetric, int diag_shift, cudaStream_t st);
 
 }  // namespace sc
 
@@ -93,7 +93,7 @@ extern "C" int sc_affinity_cosine(sc_context* ctx, int engine, int precision, co
              "sc_affinity_cosine: the tcgen05 engine needs the split fp16 planes");
   return gemm_nt_tcgen05(ctx, 1, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, d, a, lda,
-                         rowmax_offdiag, /*symmetric=*/false, as_stream(stream));
+                         rowmax_offdiag, /*symmetric=*/false, /*diag_shift=*/0, as_stream(stream));
 }
 
 extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y,
@@ -109,5 +109,31 @@ extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const floa
              "sc_diffuse: the tcgen05 engine needs the split fp16 planes");
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, n, s, lds, nullptr,
-                         /*symmetric=*/true, as_stream(stream));
+                         /*symmetric=*/true, /*diag_shift=*/0, as_stream(stream));
+}
+
+// ---- row-block / general variants used by the row-sharded multi-GPU pipeline ----------------
+extern "C" int sc_affinity_cosine_block(sc_context* ctx, int precision, const void* hi,
+                                        const void* lo, int64_t ldh, int64_t n, int64_t d,
+                                        int64_t row_begin, int64_t row_count, float* a_block,
+                                        int64_t lda, float* rowmax_offdiag_block, void* stream) {
+  SC_REQUIRE(ctx && hi && a_block && n > 0 && d > 0 && row_begin >= 0 && row_count > 0 &&
+             row_begin + row_count <= n, "sc_affinity_cosine_block: bad arguments");
+  SC_REQUIRE(lo || precision == SC_GEMM_SINGLE, "sc_affinity_cosine_block: lo plane missing");
+  const __half* h = (const __half*)hi;
+  const __half* l = (const __half*)lo;
+  return gemm_nt_tcgen05(ctx, 1, precision, h + row_begin * ldh, l ? l + row_begin * ldh : nullptr,
+                         ldh, h, l, ldh, row_count, n, d, a_block, lda, rowmax_offdiag_block,
+                         /*symmetric=*/false, /*diag_shift=*/(int)row_begin, as_stream(stream));
+}
+
+extern "C" int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi,
+                                 const void* a_lo, int64_t lda, int64_t m, const void* b_hi,
+                                 const void* b_lo, int64_t ldb, int64_t n, int64_t k, float* c,
+                                 int64_t ldc, void* stream) {
+  SC_REQUIRE(ctx && a_hi && b_hi && c && m > 0 && n > 0 && k > 0, "sc_gemm_nt_planes: bad arguments");
+  SC_REQUIRE((a_lo && b_lo) || precision == SC_GEMM_SINGLE, "sc_gemm_nt_planes: lo planes missing");
+  return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)a_hi, (const __half*)a_lo, lda,
+                         (const __half*)b_hi, (const __half*)b_lo, ldb, m, n, k, c, ldc, nullptr,
+                         /*symmetric=*/true, /*diag_shift=*/0, as_stream(stream));
 }

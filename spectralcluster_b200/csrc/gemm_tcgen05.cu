@@ -201,7 +201,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_b_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ TileTable tab, int M, int N, int K,
-               float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag) {
+               float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
+               int diag_shift) {
   constexpr int STAGES = SPLIT ? 2 : 4;
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
@@ -367,7 +368,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
           sum[i] = (sum[i] + 1.0f) * 0.5f;                 // utils.py:39
-          if (col0 + i != row && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
+          if (col0 + i != row + diag_shift && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
         }
       }
       if (row < M) {
@@ -461,7 +462,7 @@ static void build_tile_table(TileTable& tab, int tiles_m, int tiles_n) {
 template <bool SPLIT, int EPI, bool SYM>
 static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
                   const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
-                  int64_t ldc, float* rowmax, cudaStream_t st) {
+                  int64_t ldc, float* rowmax, int diag_shift, cudaStream_t st) {
   constexpr int STAGES = SPLIT ? 2 : 4;
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -478,7 +479,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     tiles = tab.num_tiles;
   }
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax); sc::launched();
+  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -486,7 +487,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, bool symmetric, cudaStream_t st) {
+                    float* rowmax_offdiag, bool symmetric, int diag_shift, cudaStream_t st) {
   SC_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31),
              "tcgen05 GEMM: bad shape");
   SC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0,
@@ -506,7 +507,7 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
   // C = Y Y^T is symmetric when both operands are the same matrix: compute the upper tiles only
   const bool sym = symmetric && a_hi == b_hi && a_lo == b_lo && M == N && lda == ldb;
 #define SC_TC_LAUNCH(SP, EP, SY) \
-  return launch<SP, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, st)
+  return launch<SP, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, diag_shift, st)
   if (split) {
     if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(true, TC_EPI_AFFINITY, true); SC_TC_LAUNCH(true, TC_EPI_AFFINITY, false); }
     if (sym) SC_TC_LAUNCH(true, TC_EPI_PLAIN, true);

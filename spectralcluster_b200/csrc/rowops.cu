@@ -196,7 +196,7 @@ __global__ void k_split_planes(const float* __restrict__ a, int64_t n, int64_t l
 }
 
 // ------------------------------------------------------------------ row statistics
-__global__ void k_row_stats(const float* __restrict__ a, int64_t n, int64_t lda,
+__global__ void k_row_stats(const float* __restrict__ a, int64_t n /*columns*/, int64_t lda,
                             double* __restrict__ rowmax, double* __restrict__ rowsum) {
   __shared__ double red[32];
   const int64_t i = blockIdx.x;
@@ -327,6 +327,15 @@ extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t 
                             double* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && a && n > 0, "sc_row_stats: bad arguments");
   k_row_stats<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, rowmax, rowsum); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows, int64_t cols,
+                                  int64_t lda, double* rowmax, double* rowsum, void* stream) {
+  SC_REQUIRE(ctx && a && rows > 0 && cols > 0, "sc_row_stats_block: bad arguments");
+  k_row_stats<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(a, cols, lda, rowmax, rowsum);
+  sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
