@@ -39,11 +39,15 @@ def parse():
   ap.add_argument("--steps", type=int, default=3)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-  ap.add_argument("--n", type=int, default=65536)
+  ap.add_argument("--n", "--size", dest="n", type=int, default=65536)
   ap.add_argument("--d", type=int, default=256)
   ap.add_argument("--speakers", type=int, default=6)
   ap.add_argument("--cpu-sample-n", type=int, default=2048)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--workload", default="predict", choices=["predict", "sharded-refine"],
+                  help="predict: BASELINE configs[2] (default, replicas over GPUs); "
+                       "sharded-refine: configs[3], ONE problem row-sharded over the GPUs, timed "
+                       "region = affinity -> ... -> Diffuse -> row statistics (no eigensolve)")
   return ap.parse_args()
 
 
@@ -168,6 +172,66 @@ def run_reference(args, rank):
   print(json.dumps(line))
 
 
+def run_sharded(args, eng, rank, world, dist):
+  """configs[3]: one N x N problem, rows sharded over the ranks (spectralcluster_b200/sharded.py)."""
+  import torch
+  import spectralcluster_b200 as scb
+  from oracle import spectral_oracle as orc
+  from spectralcluster_b200 import _native as nat
+  from spectralcluster_b200 import sharded
+  n, d = args.n, args.d
+  x = torch.from_numpy(orc.synthetic_dvectors(n, d, 8, seed=0).astype(np.float32)).to(eng.device)
+  opt = scb.RefinementOptions(gaussian_blur_sigma=1, p_percentile=0.95,
+                              thresholding_soft_multiplier=0.01,
+                              refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
+  refiner = sharded.ShardedRefiner(sharded.DeviceBackend(eng), opt,
+                                   dist=dist if world > 1 else None)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(args.warmup):
+    res = refiner.run(x, world, rank)
+    del res
+  barrier()
+  launches0 = nat.load().sc_launch_count()
+  eng.start_profile()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  start.record()
+  for _ in range(args.steps):
+    res = refiner.run(x, world, rank)
+    del res
+  stop.record()
+  barrier()
+  ms = start.elapsed_time(stop)
+  stages = eng.stop_profile()
+  launches = nat.load().sc_launch_count() - launches0
+  if world > 1:
+    tt = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0])
+  if rank == 0:
+    per = ms / args.steps
+    gemm_ms = stages.get("sc_gemm_nt_planes", 0.0) / args.steps
+    print(json.dumps({
+        "metric": "embeddings/sec through the row-sharded refinement (affinity..Diffuse..row stats)",
+        "value": n / (per / 1e3), "unit": "embeddings/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 storage; fp16x3 split tensor-core products", "data": "synthetic",
+        "config": {"workload": "N=%d d=%d ICASSP2018 refinement through Diffuse + row statistics, "
+                               "row-sharded over %d GPU(s) (BASELINE configs[3])" % (n, d, world),
+                   "parallelism": "row-shard x%d, broadcast of Y row blocks overlapped with per-peer GEMMs" % world},
+        "gpu_launches": int(launches),
+        "stage_ms_rank0": {k: v / args.steps for k, v in sorted(stages.items())},
+        "roofline": {"kernel": "k_gemm_tcgen05 (per-peer Diffuse blocks, rank 0)", "bound": "tensor",
+                     "achieved": (2.0 * n * n * n / world) / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+                     "unit": "TFLOP/s", "traffic": None}}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   args = parse()
   rank = int(os.environ.get("RANK", "0"))
@@ -185,9 +249,14 @@ def main():
 
   torch.cuda.set_device(local_rank)
   if world > 1:
+    # keep stdout to the single JSON line (NCCL prints its version banner there at INFO/VERSION)
+    os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   eng = dev.Engine.get(local_rank)
   n, d = args.n, args.d
+  if args.workload == "sharded-refine":
+    run_sharded(args, eng, rank, world, dist)
+    return
   # every rank clusters its own batch (different seed): weak scaling over independent units
   x = orc.synthetic_dvectors(n, d, args.speakers, seed=rank).astype(np.float32)
   x_pinned = torch.from_numpy(x).pin_memory()

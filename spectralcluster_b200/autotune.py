@@ -61,8 +61,12 @@ class AutoTune:
           winner = (vectors, k, p, position)
       if len(grid) <= 1 or self.search_step < MIN_SEARCH_STEP:
         break
-      reach = max(2, len(grid) // 8)
-      first = max(0, winner[3] - reach)
-      last = min(len(grid) - 1, winner[3] + reach)
-      grid = self.update_percentile_range(grid[first], grid[last], self.search_step / 2)
+      grid = self.narrow(grid, winner[3])
     return winner[0], winner[1], winner[2]
+
+  def narrow(self, grid: typing.Sequence[float], best_index: int) -> typing.Sequence[float]:
+    """Next level's grid around the winner: +-max(2, len/8) points, half the step (stored)."""
+    reach = max(2, len(grid) // 8)
+    first = max(0, best_index - reach)
+    last = min(len(grid) - 1, best_index + reach)
+    return self.update_percentile_range(grid[first], grid[last], self.search_step / 2)

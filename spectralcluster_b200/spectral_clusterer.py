@@ -80,6 +80,10 @@ class SpectralClusterer:
     self.post_eigen_cluster_function = post_eigen_cluster_function
     # Diagnostics of the last predict(): eigenvalues used by the eigengap, cluster count, solver.
     self.last_details: typing.Dict[str, typing.Any] = {}
+    # Set to a torch.distributed process group (or True for the default group) to spread the
+    # AutoTune grid over the ranks, one p_percentile evaluation at a time per GPU
+    # (BASELINE.json configs[4]); every rank must call predict() with the same embeddings.
+    self.autotune_group = None
 
   # ------------------------------------------------------------------ eigen stage
   def _eigen_on_device(self, eng, affinity: DeviceAffinity):
@@ -200,12 +204,18 @@ class SpectralClusterer:
           return (1 - p_percentile) / gap, vectors, k
         raise ValueError("Unsupported value of AutoTuneProxy")
 
+      if self.autotune_group is not None:
+        return self._predict_parallel_autotune(eng, affinity, p_percentile_to_ratio)
       eigenvectors, n_clusters, best_p = self.autotune.tune(p_percentile_to_ratio)
       self.last_details["best_p_percentile"] = best_p
     else:
       eigenvectors, n_clusters, _ = self._compute_eigenvectors_ncluster(affinity)
     del affinity
 
+    return self._cluster_embeddings(eng, eigenvectors, n_clusters)
+
+  def _cluster_embeddings(self, eng, eigenvectors, n_clusters):
+    """spectral_clusterer.py:295-313: clamp k, slice, optional row renorm, k-means."""
     if self.min_clusters is not None:
       n_clusters = max(n_clusters, self.min_clusters)
     self.last_details["n_clusters"] = n_clusters
@@ -220,3 +230,38 @@ class SpectralClusterer:
     return self.post_eigen_cluster_function(
         spectral_embeddings=spectral.to("cpu").numpy(), n_clusters=n_clusters,
         custom_dist=self.custom_dist, max_iter=self.max_iter)
+
+  def _predict_parallel_autotune(self, eng, affinity, p_percentile_to_ratio):
+    """One p_percentile per rank: rank r evaluates grid[r::world] on its own copy of the base
+    affinity; the (ratio, k) pairs are all-gathered, every rank picks the same winner, the rank
+    that evaluated it runs k-means and broadcasts the labels."""
+    import torch.distributed as dist
+    from . import sharded
+    t = dev.torch()
+    if self.autotune.search_level != 1:
+      raise NotImplementedError("parallel AutoTune supports search_level == 1")
+    group = None if self.autotune_group is True else self.autotune_group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    grid = self.autotune.get_percentile_range()
+    kept = {}
+
+    def evaluate(p):
+      ratio, vectors, k = p_percentile_to_ratio(p)
+      if not kept or ratio < kept["ratio"]:
+        kept.update(ratio=ratio, vectors=vectors, k=k, p=p)
+      return ratio, k
+
+    best, best_p, ratio, k, owner = sharded.parallel_autotune(
+        evaluate, grid, dist=dist, group=group, world=world, rank=rank)
+    if len(grid) > 1 and self.autotune.search_step >= autotune_lib.MIN_SEARCH_STEP:
+      self.autotune.narrow(grid, best)          # the reference stores the narrowed range (A.4-2)
+    self.last_details["best_p_percentile"] = best_p
+    n = affinity.n
+    on_gpu = dist.get_backend(group) == "nccl"
+    labels = t.empty((n,), dtype=t.int64, device=eng.device if on_gpu else "cpu")
+    if rank == owner:
+      assert kept["p"] == best_p
+      labels.copy_(t.from_numpy(self._cluster_embeddings(eng, kept["vectors"], kept["k"])))
+    dist.broadcast(labels, src=dist.get_global_rank(group, owner) if group is not None else owner,
+                   group=group)
+    return labels.cpu().numpy()

@@ -85,3 +85,42 @@ def test_two_ranks_match_unsharded():
   out = ctx.Queue()
   mp.spawn(_worker, args=(2, port, 2304, use_nccl, out), nprocs=2, join=True)
   assert out.get(timeout=30) <= 2e-6
+
+
+def _autotune_worker(rank, world, port, use_nccl, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(rank if use_nccl else 0)
+  dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import spectralcluster_b200 as scb
+  from conftest import load_golden
+  from test_gpu_predict import make_clusterer
+  case = load_golden("config5_autotune_n1024_d256")
+  c = make_clusterer(case["options"])
+  c.autotune_group = True
+  labels = c.predict(case["embeddings"])
+  ok = (np.array_equal(scb.utils.enforce_ordered_labels(labels),
+                       scb.utils.enforce_ordered_labels(case["labels"])) and
+        c.last_details["best_p_percentile"] == float(case["p_best"]))
+  flags = torch.tensor([1 if ok else 0], device="cuda" if use_nccl else "cpu")
+  dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+  if rank == 0:
+    out.put(int(flags[0]))
+  dist.destroy_process_group()
+
+
+def test_parallel_autotune_two_ranks_matches_reference_fixture():
+  """BASELINE.json configs[4] scaled: 8 p values over 2 ranks -> the reference's p and labels."""
+  import torch
+  import torch.multiprocessing as mp
+  use_nccl = torch.cuda.device_count() >= 2
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  ctx = mp.get_context("spawn")
+  out = ctx.Queue()
+  mp.spawn(_autotune_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
+  assert out.get(timeout=30) == 1
