@@ -13,6 +13,8 @@
 // the configuration every BASELINE config uses) and k_blur_generic (run-time radius <= 64).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace sc {
 
 constexpr int kMaxRadius = 64;
@@ -33,6 +35,7 @@ struct BlurArgs {
   const float* m;          // row maxima of the blurred matrix
   float p, mult;
   int binarize, preserve_diag, sym_type, stats_zero_diag;
+  int tiles_per_cta;       // column tiles swept by one CTA of k_blur_band (cp.async pipeline)
   float* y;
   int64_t ldy;
   __half* hi;
@@ -134,239 +137,276 @@ k_blur_generic(const BlurArgs g, const BlurWeights bw) {
 }
 
 // ------------------------------------------------------------------ compile-time radius
-// Tile 32 x 128 outputs, 256 threads.  Vertical pass: one thread per (column, 8-row strip)
-// slides a register window down the column (2 LDS per output instead of 2R+1) and stores the
-// result TRANSPOSED (pitch 33) so that the horizontal pass -- one thread per (row, 8-column
-// strip), lanes along rows -- is bank-conflict free as well.  The outputs are staged back
-// through shared memory so that the global writes (and the epilogue) are coalesced by row.
-constexpr int TTH = 32, TTW = 128, TTHREADS = 256, STRIP = 8;
+// Tile = 32 x 128 outputs, 288 threads (9 warps), two barriers per tile:
+//   fill      (40 x 136 halo'd input, 128-bit global loads into shared memory)
+//   vertical  thread = (column, 16-row strip): a 24-deep register window slides down the column;
+//             lanes run along columns -> conflict-free reads of `in`, conflict-free writes of `mid`
+//   horizontal thread = (row, 16-column strip): 24-deep window along the row of `mid` (pitch 137,
+//             odd, so lanes running along rows hit 32 different banks); the 16 outputs stay in
+//             registers and go straight into the epilogue -- 64 contiguous bytes of fp32 (or 32 B
+//             per fp16 plane) per thread, whole 32-byte sectors, no staging pass.
+// Shared-memory traffic: ~22 B per output element (was ~34 with the transposed staging), i.e.
+// below the 4+8 B/element of HBM traffic the two passes of the fused chain are allowed.
+constexpr int TTH = 32, TTW = 128, TTHREADS = 288, VSTRIP = 16, HSTRIP = 16;
 
-// Four consecutive outputs (i, j..j+3) of the threshold/symmetrize epilogue.
-__device__ __forceinline__ void thrsym4(const BlurArgs& g, int64_t i, int64_t j, const float (&b)[4],
-                                        bool full) {
-  const float mi = g.m[i];
-  float mj[4];
-  if (full) {
-    const float4 q = *reinterpret_cast<const float4*>(g.m + j);
-    mj[0] = q.x; mj[1] = q.y; mj[2] = q.z; mj[3] = q.w;
-  } else {
+template <int EPI>
+__device__ __forceinline__ void epilogue16(const BlurArgs& g, int64_t i, int64_t j0,
+                                           const float (&b)[HSTRIP], float& rmax) {
+  const bool full = (j0 + HSTRIP <= g.n);
+  if (EPI == EPI_STATS) {
+    float v = rmax;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) mj[t] = (j + t < g.n) ? g.m[j + t] : 0.0f;
+    for (int t = 0; t < HSTRIP; ++t) {
+      float x = b[t];
+      if (!full && j0 + t >= g.n) x = 0.0f;
+      if (g.stats_zero_diag && i == j0 + t) x = 0.0f;   // RowWiseThreshold preserve_diagonal
+      v = fmaxf(v, x);
+    }
+    rmax = v;
+    return;
   }
-  float y[4];
+  const int64_t io = i - g.out_row_base;
+  if (EPI == EPI_STORE) {
+    float* dst = g.out + io * g.ldo + j0;
+    if (full) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float t1 = threshold_rule(b[t], mi, g.p, g.mult, g.binarize);
-    const float t2 = threshold_rule(b[t], mj[t], g.p, g.mult, g.binarize);
-    y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
-    if (g.preserve_diag && i == j + t) y[t] = 1.0f;                  // refinement.py:208-209
+      for (int q = 0; q < HSTRIP / 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) =
+            make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < HSTRIP; ++t)
+        if (j0 + t < g.n) dst[t] = b[t];
+    }
+    if (g.rowmax_out) {
+      float v = 0.0f;
+#pragma unroll
+      for (int t = 0; t < HSTRIP; ++t)
+        if (full || j0 + t < g.n) v = fmaxf(v, b[t]);
+      atomic_max_nonneg(g.rowmax_out + i, v);
+    }
+    return;
+  }
+  // EPI_THRSYM: y = sym(thr(b, m_i), thr(b, m_j))  
+  const float cut_i = g.m[i] * g.p;
+  float y[HSTRIP];
+#pragma unroll
+  for (int q = 0; q < HSTRIP / 4; ++q) {
+    float mj[4];
+    if (full) {
+      const float4 v = *reinterpret_cast<const float4*>(g.m + j0 + 4 * q);   // warp-broadcast
+      mj[0] = v.x; mj[1] = v.y; mj[2] = v.z; mj[3] = v.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) mj[t] = (j0 + 4 * q + t < g.n) ? g.m[j0 + 4 * q + t] : 0.0f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float x = b[4 * q + t];
+      const float keep = g.binarize ? 1.0f : x;
+      const float small = x * g.mult;
+      const float t1 = (x < cut_i) ? small : keep;
+      const float t2 = (x < mj[t] * g.p) ? small : keep;
+      y[4 * q + t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
+    }
+  }
+  if (g.preserve_diag) {
+#pragma unroll
+    for (int t = 0; t < HSTRIP; ++t)
+      if (i == j0 + t) y[t] = 1.0f;                       // refinement.py:208-209
   }
   if (full) {
-    const int64_t io = i - g.out_row_base;
-    if (g.y) *reinterpret_cast<float4*>(g.y + io * g.ldy + j) = make_float4(y[0], y[1], y[2], y[3]);
+    if (g.y) {
+      float* dst = g.y + io * g.ldy + j0;
+#pragma unroll
+      for (int q = 0; q < HSTRIP / 4; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) =
+            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+    }
     if (g.hi) {
-      const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y);
-      const __half2 l23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
-      uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(g.hi + io * g.ldh + j) = hv;
-      *reinterpret_cast<uint2*>(g.lo + io * g.ldh + j) = lv;
+      uint32_t hw[HSTRIP / 2], lw[HSTRIP / 2];
+#pragma unroll
+      for (int q = 0; q < HSTRIP / 2; ++q) {
+        const __half2 h = __floats2half2_rn(y[2 * q], y[2 * q + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(y[2 * q] - f.x, y[2 * q + 1] - f.y);
+        hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[q] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      uint4* hd = reinterpret_cast<uint4*>(g.hi + io * g.ldh + j0);
+      uint4* ld = reinterpret_cast<uint4*>(g.lo + io * g.ldh + j0);
+      hd[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      hd[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      ld[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      ld[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
     }
   } else {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (j + t >= g.n) continue;
-      const int64_t io = i - g.out_row_base;
-      if (g.y) g.y[io * g.ldy + j + t] = y[t];
+    for (int t = 0; t < HSTRIP; ++t) {
+      if (j0 + t >= g.n) continue;
+      if (g.y) g.y[io * g.ldy + j0 + t] = y[t];
       if (g.hi) {
         __half h, l;
         split_half(y[t], h, l);
-        g.hi[io * g.ldh + j + t] = h;
-        g.lo[io * g.ldh + j + t] = l;
+        g.hi[io * g.ldh + j0 + t] = h;
+        g.lo[io * g.ldh + j0 + t] = l;
       }
     }
   }
 }
 
-// One 32 x 128 output tile.  `rmax` (EPI_STATS only) holds this lane's running maxima of rows
-// warp, warp+8, warp+16, warp+24 of the band.
-template <int R, int EPI>
-__device__ __forceinline__ void blur_tile_body(const BlurArgs& g, const float (&w)[2 * R + 1],
-                                               int64_t row0, int64_t col0, float* smem,
-                                               float (&rmax)[4]) {
-  constexpr int IW = TTW + 2 * R, IH = TTH + 2 * R;
-  constexpr int MP = TTH + 1;                         // transposed pitch
-  constexpr int OP = TTW + 1;                         // output staging pitch
-  static_assert(IW % 4 == 0 && R % 4 == 0, "vector fill needs 16-byte aligned tile origins");
-  float* in = smem;                                    // [IH][IW]; reused as out [TTH][OP]
-  float* midT = smem + IH * IW;                        // [IW][MP]
-  const bool interior = (row0 >= R) && (col0 >= R) && (row0 + TTH + R <= g.n) &&
-                        (col0 + TTW + R <= g.n);
-  const bool vec_ok = interior && ((g.lda & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g.a) & 15) == 0);
-  if (vec_ok) {
-    const float* src = g.a + (row0 - R - g.in_row_base) * g.lda + (col0 - R);
-    for (int idx = threadIdx.x; idx < IH * (IW / 4); idx += TTHREADS) {
-      const int r = idx / (IW / 4), q = idx - r * (IW / 4);
-      *reinterpret_cast<float4*>(in + r * IW + 4 * q) =
-          *reinterpret_cast<const float4*>(src + (int64_t)r * g.lda + 4 * q);
-    }
-    if (g.diag) {
-      // fused CropDiagonal: patch the diagonal elements that fall inside the halo'd tile
-      const int64_t lo = (row0 > col0 ? row0 : col0) - R;
-      const int64_t hi = ((row0 + TTH < col0 + TTW) ? row0 + TTH : col0 + TTW) + R;
-      if (lo < hi) {                                   // block-uniform
-        __syncthreads();
-        for (int64_t d = lo + threadIdx.x; d < hi; d += TTHREADS)
-          in[(d - (row0 - R)) * IW + (d - (col0 - R))] = g.diag[d];
-      }
-    }
-  } else {
-    for (int idx = threadIdx.x; idx < IH * IW; idx += TTHREADS) {
-      const int r = idx / IW, c = idx - r * IW;
-      int64_t gr = row0 - R + r, gc = col0 - R + c;
-      if (!interior) {
-        gr = reflect_index(gr, g.n);
-        gc = reflect_index(gc, g.n);
-      }
-      in[idx] = load_input(g, gr, gc);
-    }
-  }
-  __syncthreads();
-  // vertical: items = IW columns x (TTH/STRIP) strips
-  for (int item = threadIdx.x; item < IW * (TTH / STRIP); item += TTHREADS) {
-    const int c = item % IW, r0 = (item / IW) * STRIP;
-    float win[STRIP + 2 * R];
-#pragma unroll
-    for (int k = 0; k < STRIP + 2 * R; ++k) win[k] = in[(r0 + k) * IW + c];
-#pragma unroll
-    for (int o = 0; o < STRIP; ++o) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
-      midT[c * MP + r0 + o] = acc;
-    }
-  }
-  __syncthreads();
-  // horizontal: items = TTH rows x (TTW/STRIP) strips; lanes run along rows.  All reads of
-  // `in` finished before the barrier above, so it can take the outputs.
-  float* outs = in;
-  for (int item = threadIdx.x; item < TTH * (TTW / STRIP); item += TTHREADS) {
-    const int r = item % TTH, c0 = (item / TTH) * STRIP;
-    float win[STRIP + 2 * R];
-#pragma unroll
-    for (int k = 0; k < STRIP + 2 * R; ++k) win[k] = midT[(c0 + k) * MP + r];
-#pragma unroll
-    for (int o = 0; o < STRIP; ++o) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
-      outs[r * OP + c0 + o] = acc;
-    }
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool cols_full = (col0 + TTW <= g.n);
-  if (EPI == EPI_STATS) {
-    // warp -> rows warp, warp+8, ...; lanes stride the 128 columns; maxima stay in registers
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = warp + 8 * q;
-      const int64_t i = row0 + r;
-      if (i >= g.row_end) continue;
-      float v = rmax[q];
-#pragma unroll
-      for (int u = 0; u < TTW / 32; ++u) {
-        const int c = lane + 32 * u;
-        const int64_t j = col0 + c;
-        float b = outs[r * OP + c];
-        if (!cols_full && j >= g.n) b = 0.0f;
-        if (g.stats_zero_diag && i == j) b = 0.0f;     // RowWiseThreshold preserve_diagonal
-        v = fmaxf(v, b);
-      }
-      rmax[q] = v;
-    }
-  } else {
-    // a warp = one row: lane handles 4 consecutive columns (512 B fp32 / 256 B fp16 per warp)
-    for (int r = warp; r < TTH; r += TTHREADS / 32) {
-      const int64_t i = row0 + r;
-      if (i >= g.row_end) continue;
-      const int c = lane * 4;
-      const int64_t j = col0 + c;
-      if (j >= g.n) continue;
-      float b[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) b[t] = outs[r * OP + c + t];
-      const bool full = (j + 3 < g.n);
-      if (EPI == EPI_THRSYM) {
-        thrsym4(g, i, j, b, full);
-      } else {   // EPI_STORE
-        if (full) {
-          *reinterpret_cast<float4*>(g.out + (i - g.out_row_base) * g.ldo + j) = make_float4(b[0], b[1], b[2], b[3]);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (j + t < g.n) g.out[(i - g.out_row_base) * g.ldo + j + t] = b[t];
-        }
-        if (g.rowmax_out) {
-          float v = 0.0f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (j + t < g.n) v = fmaxf(v, b[t]);
-          rmax[0] = v;   // scratch
-        }
-      }
-      if (EPI == EPI_STORE && g.rowmax_out) {
-        // (all lanes of the row reach here together only when none `continue`d; do the
-        //  reduction with the active mask)
-        const unsigned mask = __activemask();
-        float v = rmax[0];
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
-        if (lane == 0) atomic_max_nonneg(g.rowmax_out + i, v);
-      }
-    }
-  }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// one tile per CTA (EPI_STORE / EPI_THRSYM)
-template <int R, int EPI>
-__global__ void __launch_bounds__(TTHREADS)
-k_blur_tile(const BlurArgs g, const BlurWeights bw) {
-  extern __shared__ float smem[];
-  float w[2 * R + 1];
-#pragma unroll
-  for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
-  float scratch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  blur_tile_body<R, EPI>(g, w, g.row_begin + (int64_t)blockIdx.y * TTH, (int64_t)blockIdx.x * TTW, smem,
-                         scratch);
-}
-
-// statistics pass: one CTA per 32-row band sweeps all column tiles; each lane keeps running
-// maxima of its 4 rows in registers -- no atomics at all (the first version issued N^2/32 global
-// atomics onto N addresses and ran at 4% of the HBM roofline).
 template <int R>
+struct TileGeom {
+  static constexpr int IW = TTW + 2 * R, IH = TTH + 2 * R, MP = IW + 1;
+  static_assert(IW % 4 == 0 && R % 4 == 0, "vector fill needs 16-byte aligned tile origins");
+  static_assert(IW * (TTH / VSTRIP) <= TTHREADS && TTH * (TTW / HSTRIP) <= TTHREADS,
+                "one work item per thread in both passes");
+};
+
+template <int R>
+__device__ __forceinline__ bool tile_is_vec(const BlurArgs& g, int64_t row0, int64_t col0) {
+  return (row0 >= R) && (col0 >= R) && (row0 + TTH + R <= g.n) && (col0 + TTW + R <= g.n) &&
+         ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.a) & 15) == 0);
+}
+
+// Stage the halo'd input tile into `in`.  Interior tiles go through cp.async (16-byte copies
+// that complete in the background: the caller commits the group and waits before use); edge
+// tiles take the synchronous path with reflected indices.
+template <int R>
+__device__ __forceinline__ void tile_fill(const BlurArgs& g, int64_t row0, int64_t col0,
+                                          float* in) {
+  using G = TileGeom<R>;
+  const int tid = threadIdx.x;
+  if (tile_is_vec<R>(g, row0, col0)) {
+    const float* src = g.a + (row0 - R - g.in_row_base) * g.lda + (col0 - R);
+    for (int idx = tid; idx < G::IH * (G::IW / 4); idx += TTHREADS) {
+      const int r = idx / (G::IW / 4), q = idx - r * (G::IW / 4);
+      cp_async16(in + r * G::IW + 4 * q, src + (int64_t)r * g.lda + 4 * q);
+    }
+  } else {
+    for (int idx = tid; idx < G::IH * G::IW; idx += TTHREADS) {
+      const int r = idx / G::IW, c = idx - r * G::IW;
+      const int64_t gr = reflect_index(row0 - R + r, g.n), gc = reflect_index(col0 - R + c, g.n);
+      in[idx] = load_input(g, gr, gc);      // applies the diagonal override itself
+    }
+  }
+}
+
+// Both separable passes + epilogue on a staged tile.  The caller has made `in` visible to the
+// whole block (cp.async.wait_group + __syncthreads) and guarantees nobody still reads `mid`.
+template <int R, int EPI>
+__device__ __forceinline__ void tile_compute(const BlurArgs& g, const float (&w)[2 * R + 1],
+                                             int64_t row0, int64_t col0, float* in, float* mid,
+                                             float& rmax) {
+  using G = TileGeom<R>;
+  const int tid = threadIdx.x;
+  if (g.diag && tile_is_vec<R>(g, row0, col0)) {
+    // fused CropDiagonal on the vector path: patch the diagonal elements inside the halo'd tile
+    const int64_t lo = (row0 > col0 ? row0 : col0) - R;
+    const int64_t hi = ((row0 + TTH < col0 + TTW) ? row0 + TTH : col0 + TTW) + R;
+    if (lo < hi) {                                     // block-uniform
+      for (int64_t d = lo + tid; d < hi; d += TTHREADS)
+        in[(d - (row0 - R)) * G::IW + (d - (col0 - R))] = g.diag[d];
+      __syncthreads();
+    }
+  }
+  if (tid < G::IW * (TTH / VSTRIP)) {
+    const int c = tid % G::IW, r0 = (tid / G::IW) * VSTRIP;
+    float win[VSTRIP + 2 * R];
+#pragma unroll
+    for (int k = 0; k < VSTRIP + 2 * R; ++k) win[k] = in[(r0 + k) * G::IW + c];
+#pragma unroll
+    for (int o = 0; o < VSTRIP; ++o) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
+      mid[(r0 + o) * G::MP + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < TTH * (TTW / HSTRIP)) {
+    const int r = tid % TTH, c0 = (tid / TTH) * HSTRIP;
+    float win[HSTRIP + 2 * R];
+#pragma unroll
+    for (int k = 0; k < HSTRIP + 2 * R; ++k) win[k] = mid[r * G::MP + c0 + k];
+    float b[HSTRIP];
+#pragma unroll
+    for (int o = 0; o < HSTRIP; ++o) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
+      b[o] = acc;
+    }
+    const int64_t i = row0 + r, j0 = col0 + c0;
+    if (i < g.row_end && j0 < g.n) epilogue16<EPI>(g, i, j0, b, rmax);
+  }
+}
+
+// One CTA per 32-row band, sweeping the column tiles with a 2-deep cp.async pipeline: the loads
+// of tile t+1 are in flight while tile t is filtered, so every resident CTA always has ~22 KB
+// outstanding (3 CTAs/SM) -- the first, load-then-compute version left HBM idle during the two
+// filter passes and ran latency-bound at ~28% of the roofline.
+//   EPI_STATS : row maxima of the blurred band, one register per thread, no atomics
+//   EPI_THRSYM/EPI_STORE : the band's output rows
+template <int R, int EPI>
 __global__ void __launch_bounds__(TTHREADS)
-k_blur_band_stats(const BlurArgs g, const BlurWeights bw) {
+k_blur_band(const BlurArgs g, const BlurWeights bw) {
+  using G = TileGeom<R>;
   extern __shared__ float smem[];
+  __shared__ float part[TTW / HSTRIP][TTH];
+  float* in0 = smem;
+  float* in1 = smem + G::IH * G::IW;
+  float* mid = smem + 2 * G::IH * G::IW;
   float w[2 * R + 1];
 #pragma unroll
   for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
-  float rmax[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float rmax = 0.0f;
   const int64_t row0 = g.row_begin + (int64_t)blockIdx.x * TTH;
-  const int ntx = (int)((g.n + TTW - 1) / TTW);
-  for (int tx = 0; tx < ntx; ++tx) {
-    __syncthreads();                                   // previous tile's readers are done
-    blur_tile_body<R, EPI_STATS>(g, w, row0, (int64_t)tx * TTW, smem, rmax);
+  // blockIdx.y selects a run of `tiles_per_cta` column tiles of the band
+  const int ntiles = (int)((g.n + TTW - 1) / TTW);
+  const int tx0 = blockIdx.y * g.tiles_per_cta;
+  const int ntx = min(ntiles, tx0 + g.tiles_per_cta);
+  tile_fill<R>(g, row0, (int64_t)tx0 * TTW, in0);
+  cp_async_commit();
+  for (int tx = tx0; tx < ntx; ++tx) {
+    float* cur = ((tx - tx0) & 1) ? in1 : in0;
+    float* nxt = ((tx - tx0) & 1) ? in0 : in1;
+    if (tx + 1 < ntx) {
+      tile_fill<R>(g, row0, (int64_t)(tx + 1) * TTW, nxt);   // `nxt` was last read two tiles ago
+      cp_async_commit();
+      cp_async_wait<1>();                                     // tile tx has landed
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // tile tx visible; everybody is out of the previous horizontal pass
+    tile_compute<R, EPI>(g, w, row0, (int64_t)tx * TTW, cur, mid, rmax);
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (EPI == EPI_STATS) {
+    if (threadIdx.x < TTH * (TTW / HSTRIP)) part[threadIdx.x / TTH][threadIdx.x % TTH] = rmax;
+    __syncthreads();
+    if (threadIdx.x < TTH) {
+      float v = 0.0f;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float v = warp_max(rmax[q]);
-    const int64_t i = row0 + warp + 8 * q;
-    if (lane == 0 && i < g.row_end) g.rowmax_out[i] = v;
+      for (int s8 = 0; s8 < TTW / HSTRIP; ++s8) v = fmaxf(v, part[s8][threadIdx.x]);
+      const int64_t i = row0 + threadIdx.x;
+      if (i < g.row_end) {
+        if (gridDim.y == 1) g.rowmax_out[i] = v;
+        else atomic_max_nonneg(g.rowmax_out + i, v);   // few segments per band; caller zero-fills
+      }
+    }
   }
 }
 
@@ -420,21 +460,22 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
   }
   if (radius == 4) {
     constexpr int R = 4;
-    const size_t smem = sizeof(float) * ((TTH + 2 * R) * (TTW + 2 * R) + (TTW + 2 * R) * (TTH + 1));
-    static_assert((TTH + 2 * R) * (TTW + 2 * R) >= TTH * (TTW + 1), "output staging must fit");
-    if (EPI == EPI_STATS) {
-      auto kband = k_blur_band_stats<R>;
-      SC_CUDA(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kband<<<(unsigned)((g.row_end - g.row_begin + TTH - 1) / TTH), TTHREADS, smem, st>>>(g, bw);
-      sc::launched();
-      SC_LAUNCH_CHECK();
-      return 0;
+    const size_t smem = sizeof(float) * (2 * (TTH + 2 * R) * (TTW + 2 * R) +
+                                         TTH * (TTW + 2 * R + 1));
+    auto kband = k_blur_band<R, EPI>;
+    SC_CUDA(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (int)((g.n + TTW - 1) / TTW);
+    static int tpc_env = -1;
+    if (tpc_env < 0) {
+      const char* e = getenv("SCB_BLUR_TILES_PER_CTA");
+      tpc_env = e ? atoi(e) : 0;
     }
-    auto kern = k_blur_tile<R, EPI>;
-    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const dim3 grid((unsigned)((g.n + TTW - 1) / TTW),
-                    (unsigned)((g.row_end - g.row_begin + TTH - 1) / TTH));
-    kern<<<grid, TTHREADS, smem, st>>>(g, bw); sc::launched();
+    g.tiles_per_cta = tpc_env > 0 ? tpc_env : 4;
+    if (g.tiles_per_cta > ntiles) g.tiles_per_cta = ntiles;
+    const unsigned gy = (unsigned)((ntiles + g.tiles_per_cta - 1) / g.tiles_per_cta);
+    const dim3 grid((unsigned)((g.row_end - g.row_begin + TTH - 1) / TTH), gy);
+    kband<<<grid, TTHREADS, smem, st>>>(g, bw);
+    sc::launched();
     SC_LAUNCH_CHECK();
     return 0;
   }
