@@ -44,7 +44,7 @@ def parse():
   ap.add_argument("--speakers", type=int, default=6)
   ap.add_argument("--cpu-sample-n", type=int, default=2048)
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--workload", default="predict", choices=["predict", "sharded-refine"],
+  ap.add_argument("--workload", default="predict", choices=["predict", "sharded-refine", "sharded-predict"],
                   help="predict: BASELINE configs[2] (default, replicas over GPUs); "
                        "sharded-refine: configs[3], ONE problem row-sharded over the GPUs, timed "
                        "region = affinity -> ... -> Diffuse -> row statistics (no eigensolve)")
@@ -200,13 +200,17 @@ def run_sharded(args, eng, rank, world, dist):
   eng.start_profile()
   start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   start.record()
-  for _ in range(args.steps):
+  for step in range(args.steps):
+    if step == args.steps - 1:
+      refiner.trace = []
     res = refiner.run(x, world, rank)
     del res
   stop.record()
   barrier()
   ms = start.elapsed_time(stop)
   stages = eng.stop_profile()
+  trace = refiner.trace or []
+  timeline = {trace[i][0]: trace[0][1].elapsed_time(trace[i][1]) for i in range(1, len(trace))}
   launches = nat.load().sc_launch_count() - launches0
   if world > 1:
     tt = torch.tensor([ms], dtype=torch.float64, device=eng.device)
@@ -225,9 +229,66 @@ def run_sharded(args, eng, rank, world, dist):
                    "parallelism": "row-shard x%d, broadcast of Y row blocks overlapped with per-peer GEMMs" % world},
         "gpu_launches": int(launches),
         "stage_ms_rank0": {k: v / args.steps for k, v in sorted(stages.items())},
+        "timeline_ms_rank0_last_step": timeline,
         "roofline": {"kernel": "k_gemm_tcgen05 (per-peer Diffuse blocks, rank 0)", "bound": "tensor",
                      "achieved": (2.0 * n * n * n / world) / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                      "unit": "TFLOP/s", "traffic": None}}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def run_sharded_predict(args, eng, rank, world, dist):
+  """One N x N problem end to end (predict) with every matrix row-sharded over the ranks."""
+  import torch
+  from oracle import spectral_oracle as orc
+  from spectralcluster_b200 import _native as nat
+  from spectralcluster_b200 import sharded
+  n, d = args.n, args.d
+  x, truth = orc.synthetic_dvectors(n, d, args.speakers, seed=0, return_labels=True)
+  x = x.astype(np.float32)
+  clusterer = make_clusterer()
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  labels = None
+  for _ in range(args.warmup):
+    labels = sharded.predict_sharded(clusterer, x, dist=dist if world > 1 else None)
+  barrier()
+  launches0 = nat.load().sc_launch_count()
+  eng.start_profile()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    labels = sharded.predict_sharded(clusterer, x, dist=dist if world > 1 else None)
+  barrier()
+  sec = time.perf_counter() - t0
+  stages = eng.stop_profile()
+  launches = nat.load().sc_launch_count() - launches0
+  if world > 1:
+    tt = torch.tensor([sec], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt[0])
+  if rank == 0:
+    from spectralcluster_b200 import utils
+    correct = bool(np.array_equal(utils.enforce_ordered_labels(labels),
+                                  utils.enforce_ordered_labels(truth)))
+    per = sec / args.steps
+    print(json.dumps({
+        "metric": "embeddings/sec through predict() (row-sharded)", "value": n / per,
+        "unit": "embeddings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 storage; fp16x3 split tensor-core products; f64 eigensolve",
+        "data": "synthetic",
+        "config": {"workload": workload_name(n, d) + "; ONE problem row-sharded over %d GPU(s)" % world,
+                   "labels_match_generator_truth": correct,
+                   "details": {k: (v.tolist() if hasattr(v, "tolist") else v)
+                               for k, v in clusterer.last_details.items()}},
+        "e2e": {"value": n / per, "unit": "embeddings/s", "h2d_bytes_per_step": int(x.nbytes),
+                "d2h_bytes_per_step": int(labels.nbytes)},
+        "gpu_launches": int(launches),
+        "stage_ms_rank0": {k: v / args.steps for k, v in sorted(stages.items())}}))
   if world > 1:
     dist.destroy_process_group()
 
@@ -256,6 +317,9 @@ def main():
   n, d = args.n, args.d
   if args.workload == "sharded-refine":
     run_sharded(args, eng, rank, world, dist)
+    return
+  if args.workload == "sharded-predict":
+    run_sharded_predict(args, eng, rank, world, dist)
     return
   # every rank clusters its own batch (different seed): weak scaling over independent units
   x = orc.synthetic_dvectors(n, d, args.speakers, seed=rank).astype(np.float32)

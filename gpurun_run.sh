@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-for t in 1 2 4 8 16 64 512; do SCB_BLUR_TILES_PER_CTA=$t timeout 300 python tools/time_blur.py --n 65536 >> gpurun_out/blur_sweep.txt 2>&1; done
-for t in 1 4 16; do SCB_BLUR_TILES_PER_CTA=$t timeout 300 python tools/time_blur.py --n 16384 >> gpurun_out/blur_sweep.txt 2>&1; done
-cat gpurun_out/blur_sweep.txt
+timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout 600 --tb=short > gpurun_out/t_sharded1.log 2>&1
+timeout 600 python bench.py --workload sharded-predict --n 65536 --steps 2 --warmup 2 > gpurun_out/sp1.json 2> gpurun_out/sp1.err
+tail -n 12 gpurun_out/t_sharded1.log; tail -c 600 gpurun_out/sp1.err; head -c 700 gpurun_out/sp1.json

@@ -61,6 +61,9 @@ long long sc_launch_count(void);
 int sc_context_create(int device, sc_context** out);
 int sc_context_destroy(sc_context* ctx);
 int sc_context_sm_count(const sc_context* ctx);
+/* Cap the CTA count of the persistent GEMM (0 = every SM) so that communication kernels issued
+ * concurrently (NCCL send/recv in the sharded pipeline) find free SMs. */
+int sc_context_set_gemm_sm_limit(sc_context* ctx, int sms);
 
 /* ---- utils.compute_affinity_matrix (utils.py:20-41) --------------------------------- */
 /* Row L2-normalisation (utils.py:32-33).  x is [n,d] fp32 (x_is_f64=0) or fp64 (=1) on the
@@ -167,6 +170,9 @@ int sc_blur_threshold_symmetrize_block(sc_context* ctx, const float* a, int64_t 
 /* Row maxima / sums of a rectangular [rows, cols] block (local rows of a sharded matrix). */
 int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows, int64_t cols, int64_t lda,
                        double* rowmax, double* rowsum, void* stream);
+/* dst[cols, rows] = src[rows, cols]^T (the mirrored S blocks exchanged between ranks). */
+int sc_transpose(sc_context* ctx, const float* src, int64_t rows, int64_t cols, int64_t lds,
+                 float* dst, int64_t ldd, void* stream);
 /* c[m,n] = (a_hi+a_lo)[m,k] (b_hi+b_lo)[n,k]^T : one (row block) x (peer row block) piece of
  * Diffuse (refinement.py:232-234) in the sharded pipeline. */
 int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi, const void* a_lo,
@@ -193,6 +199,18 @@ int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds, co
                      const double* left, const double* right, double sign, int which,
                      int64_t n_values, int64_t n_vectors, double tol, int64_t max_matvecs,
                      double* w_host, double* v_dev, int64_t* stats_host, void* stream);
+
+/* Row-sharded variant: `s_block` holds rows [row_begin, row_begin+rows) of S.  Each matvec writes
+ * y_full[row_begin .. row_begin+rows) and calls gather(user), which must all-gather y_full across
+ * the ranks on `stream` (N doubles per matvec); all other work is replicated, so every rank returns
+ * identical results.  delta/left/right and the outputs are full length, as in sc_eigh_extremal. */
+typedef int (*sc_gather_fn)(void* user);
+int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, int64_t rows, int64_t row_begin,
+                             int64_t n, int64_t lds, const double* delta, const double* left,
+                             const double* right, double sign, int which, int64_t n_values,
+                             int64_t n_vectors, double tol, int64_t max_matvecs, double* y_full,
+                             sc_gather_fn gather, void* user, double* w_host, double* v_dev,
+                             int64_t* stats_host, void* stream);
 
 /* Rows of e[n,k] (fp64) scaled to unit L2 norm (spectral_clusterer.py:301-305). In place. */
 int sc_row_renorm(sc_context* ctx, double* e, int64_t n, int64_t k, void* stream);

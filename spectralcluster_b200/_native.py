@@ -17,6 +17,7 @@ c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 c_dbl = ctypes.c_double
 c_ptr = ctypes.c_void_p
+GATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)   # sc_gather_fn
 
 # name -> argtypes (every function returns int except the two noted); this table is also what
 # tests/test_abi.py checks against include/spectralcluster_b200.h.
@@ -27,6 +28,7 @@ PROTOTYPES = {
     "sc_context_create": [c_int, ctypes.POINTER(c_ptr)],
     "sc_context_destroy": [c_ptr],
     "sc_context_sm_count": [c_ptr],
+    "sc_context_set_gemm_sm_limit": [c_ptr, c_int],
     "sc_normalize_rows": [c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
                           c_i64, c_ptr],
     "sc_affinity_cosine": [c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64,
@@ -55,12 +57,16 @@ PROTOTYPES = {
                                            c_ptr, c_dbl, c_ptr, c_dbl, c_dbl, c_int, c_int, c_int,
                                            c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_row_stats_block": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "sc_transpose": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_gemm_nt_planes": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64,
                           c_i64, c_ptr, c_i64, c_ptr],
     "sc_eigh_dense": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                       c_i64, c_ptr, c_ptr, c_ptr],
     "sc_eigh_extremal": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                          c_i64, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sc_eigh_extremal_sharded": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
+                                 c_dbl, c_int, c_i64, c_i64, c_dbl, c_i64, c_ptr, c_ptr, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr],
     "sc_row_renorm": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "sc_kmeans": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_i64, c_dbl,
                   c_ptr, c_ptr, c_ptr],

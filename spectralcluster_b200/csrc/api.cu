@@ -61,6 +61,7 @@ extern "C" int sc_context_create(int device, sc_context** out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
+  ctx->gemm_sm_limit = 0;
   // keep stream-ordered scratch inside the pool between calls (no trim at every sync)
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -77,6 +78,12 @@ extern "C" int sc_context_destroy(sc_context* ctx) {
 }
 
 extern "C" int sc_context_sm_count(const sc_context* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int sc_context_set_gemm_sm_limit(sc_context* ctx, int sms) {
+  SC_REQUIRE(ctx && sms >= 0, "sc_context_set_gemm_sm_limit: bad arguments");
+  ctx->gemm_sm_limit = sms;
+  return 0;
+}
 
 extern "C" int sc_affinity_cosine(sc_context* ctx, int engine, int precision, const float* xn,
                                   int64_t ldxn, const void* hi, const void* lo, int64_t ldh,

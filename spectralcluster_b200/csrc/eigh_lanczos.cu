@@ -28,19 +28,20 @@ constexpr int SYMV_ROWS = 8;       // rows per CTA (one warp each)
 constexpr int SYMV_CHUNK = 2048;   // multiple of 256   // columns of t staged in shared memory per step
 
 __global__ void __launch_bounds__(SYMV_ROWS * 32)
-k_symv_f32_f64(const float* __restrict__ s, int64_t n, int64_t lds, const double* __restrict__ t,
-               double* __restrict__ y) {
+k_symv_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
+               const double* __restrict__ t, double* __restrict__ y) {
+  // y[0..rows) = S[0..rows, 0..n) t   (rows == n on one GPU; a row block when sharded)
   __shared__ double ts[SYMV_CHUNK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * SYMV_ROWS + warp;
-  const float* r = s + (row < n ? row : 0) * lds;
+  const float* r = s + (row < rows ? row : 0) * lds;
   double acc0 = 0.0, acc1 = 0.0;
   for (int64_t c0 = 0; c0 < n; c0 += SYMV_CHUNK) {
     const int64_t len = (n - c0 < SYMV_CHUNK) ? (n - c0) : SYMV_CHUNK;
     __syncthreads();
     for (int64_t j = threadIdx.x; j < SYMV_CHUNK; j += blockDim.x) ts[j] = (j < len) ? t[c0 + j] : 0.0;
     __syncthreads();
-    if (row < n) {
+    if (row < rows) {
       // lanes walk consecutive columns (coalesced 128 B per warp load, conflict-free shared
       // reads); 8 independent loads in flight per lane
       const float* rc = r + c0;
@@ -57,7 +58,7 @@ k_symv_f32_f64(const float* __restrict__ s, int64_t n, int64_t lds, const double
     }
   }
   double acc = warp_sum(acc0 + acc1);
-  if (row < n && lane == 0) y[row] = acc;
+  if (row < rows && lane == 0) y[row] = acc;
 }
 
 // t = c .* x
@@ -212,11 +213,19 @@ static void jacobi_eigh(std::vector<double>& a, int m, std::vector<double>& w,
 
 using namespace sc;
 
-extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds,
-                                const double* delta, const double* left, const double* right,
-                                double sign, int which, int64_t n_values, int64_t n_vectors,
-                                double tol, int64_t max_matvecs, double* w_host, double* v_dev,
-                                int64_t* stats_host, void* stream) {
+typedef int (*sc_gather_fn)(void* user);
+
+// Shared implementation.  Unsharded: rows == n, row_begin == 0, y_ext == NULL.  Row-sharded: `s`
+// holds the rows [row_begin, row_begin+rows) of S; every matvec writes its slice of y_ext (a
+// device fp64 vector the caller owns) and calls `gather` to all-gather y_ext across the ranks
+// (N doubles of traffic per matvec); everything else runs replicated on full-length vectors, so
+// every rank takes identical decisions.
+static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t row_begin,
+                        int64_t n, int64_t lds, const double* delta, const double* left,
+                        const double* right, double sign, int which, int64_t n_values,
+                        int64_t n_vectors, double tol, int64_t max_matvecs, double* y_ext,
+                        sc_gather_fn gather, void* user, double* w_host, double* v_dev,
+                        int64_t* stats_host, void* stream) {
   SC_REQUIRE(ctx && s && w_host && n > 0, "sc_eigh_extremal: bad arguments");
   SC_REQUIRE(n_values >= 1 && n_values <= 32 && n_vectors >= 0 && n_vectors <= n_values,
              "sc_eigh_extremal: need 1 <= n_values <= 32 and n_vectors <= n_values");
@@ -241,8 +250,8 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   double* V = vb.as<double>();
   double* V2 = vb2.as<double>();
   double* t = work.as<double>();
-  double* y = t + n;
-  double* w = y + n;
+  double* y = y_ext ? y_ext : t + n;
+  double* w = t + 2 * n;
   double* h_dev = small.as<double>();          // [m+1]
   double* h2_dev = h_dev + (m + 1);            // [m+1]
   double* nrm_dev = h2_dev + (m + 1);          // [1] (+pad)
@@ -302,8 +311,12 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
     for (int i = j; i < m; ++i) {
       // w = flip * Op V_i
       k_prescale<<<gn, 256, 0, st>>>(V + (size_t)i * n, left, right, n, t); sc::launched();
-      k_symv_f32_f64<<<(unsigned)((n + SYMV_ROWS - 1) / SYMV_ROWS), SYMV_ROWS * 32, 0, st>>>(
-          s, n, lds, t, y); sc::launched();
+      k_symv_f32_f64<<<(unsigned)((rows + SYMV_ROWS - 1) / SYMV_ROWS), SYMV_ROWS * 32, 0, st>>>(
+          s, rows, n, lds, t, y + row_begin); sc::launched();
+      if (gather) {
+        SC_LAUNCH_CHECK();
+        SC_REQUIRE(gather(user) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
+      }
       k_postscale<<<gn, 256, 0, st>>>(V + (size_t)i * n, y, delta, left, right, sign, flip, n, w); sc::launched();
       ++matvecs;
       // classical Gram-Schmidt twice against V_0..V_i
@@ -397,4 +410,29 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
   SC_REQUIRE(converged >= nev, "sc_eigh_extremal: only %d of %d eigenpairs converged to %g in "
              "%lld matrix-vector products", converged, nev, tol, (long long)matvecs);
   return 0;
+}
+
+extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds,
+                                const double* delta, const double* left, const double* right,
+                                double sign, int which, int64_t n_values, int64_t n_vectors,
+                                double tol, int64_t max_matvecs, double* w_host, double* v_dev,
+                                int64_t* stats_host, void* stream) {
+  return lanczos_impl(ctx, s, n, 0, n, lds, delta, left, right, sign, which, n_values, n_vectors,
+                      tol, max_matvecs, nullptr, nullptr, nullptr, w_host, v_dev, stats_host,
+                      stream);
+}
+
+extern "C" int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, int64_t rows,
+                                        int64_t row_begin, int64_t n, int64_t lds,
+                                        const double* delta, const double* left,
+                                        const double* right, double sign, int which,
+                                        int64_t n_values, int64_t n_vectors, double tol,
+                                        int64_t max_matvecs, double* y_full, sc_gather_fn gather,
+                                        void* user, double* w_host, double* v_dev,
+                                        int64_t* stats_host, void* stream) {
+  SC_REQUIRE(s_block && y_full && gather && rows > 0 && row_begin >= 0 && row_begin + rows <= n,
+             "sc_eigh_extremal_sharded: bad arguments");
+  return lanczos_impl(ctx, s_block, rows, row_begin, n, lds, delta, left, right, sign, which,
+                      n_values, n_vectors, tol, max_matvecs, y_full, gather, user, w_host, v_dev,
+                      stats_host, stream);
 }

@@ -478,7 +478,9 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     build_tile_table(tab, tiles_m, tiles_n);
     tiles = tab.num_tiles;
   }
-  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  int sms = ctx->sm_count;
+  if (ctx->gemm_sm_limit > 0 && ctx->gemm_sm_limit < sms) sms = ctx->gemm_sm_limit;
+  const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;

@@ -171,6 +171,22 @@ __global__ void k_symmetrize(const float* __restrict__ a, int64_t n, int64_t lda
   }
 }
 
+// ------------------------------------------------------------------ transpose (rectangular)
+__global__ void k_transpose(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t lds,
+                            float* __restrict__ dst, int64_t ldd) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = r0 + r, j = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < rows && j < cols) ? src[i * lds + j] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t j = c0 + r, i = r0 + threadIdx.x;     // dst[j][i] = src[i][j]
+    if (i < rows && j < cols) dst[j * ldd + i] = tile[threadIdx.x][r];
+  }
+}
+
 // ------------------------------------------------------------------ split planes
 __global__ void k_split_planes(const float* __restrict__ a, int64_t n, int64_t lda,
                                __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldh) {
@@ -335,6 +351,17 @@ extern "C" int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows,
                                   int64_t lda, double* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && a && rows > 0 && cols > 0, "sc_row_stats_block: bad arguments");
   k_row_stats<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(a, cols, lda, rowmax, rowsum);
+  sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_transpose(sc_context* ctx, const float* src, int64_t rows, int64_t cols,
+                            int64_t lds, float* dst, int64_t ldd, void* stream) {
+  SC_REQUIRE(ctx && src && dst && rows > 0 && cols > 0 && src != dst, "sc_transpose: bad arguments");
+  const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  SC_REQUIRE(grid.y <= 65535u, "sc_transpose: too many rows");
+  k_transpose<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(src, rows, cols, lds, dst, ldd);
   sc::launched();
   SC_LAUNCH_CHECK();
   return 0;

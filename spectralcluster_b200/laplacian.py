@@ -56,13 +56,22 @@ def operator_terms(eng, refined, laplacian_type, eps: float = EPS):
   GraphCut                : M = D^ D D^ - (D^ R) S D^, D^ = 1/(sqrt(d)+eps)  (laplacian.py:56-58)
   where R = refined.row_scale (or I) and d = R * rowsum(S) (laplacian.py:41).
   """
-  t = dev.torch()
   r = refined.row_scale
   if laplacian_type is None or laplacian_type == LaplacianType.Affinity:
     return None, r, None, 1.0, nat.EIG_LARGEST
   if not isinstance(laplacian_type, LaplacianType):
     raise TypeError("laplacian_type must be a LaplacianType")
   _, rowsum = eng.row_stats(refined.s, refined.n, want_max=False, want_sum=True)
+  return terms_from_row_sums(rowsum, r, laplacian_type, eps)
+
+
+def terms_from_row_sums(rowsum, r, laplacian_type, eps: float = EPS):
+  """operator_terms given rowsum(S) (device fp64 vector) and the row scaling r (or None)."""
+  t = dev.torch()
+  if laplacian_type is None or laplacian_type == LaplacianType.Affinity:
+    return None, r, None, 1.0, nat.EIG_LARGEST
+  if not isinstance(laplacian_type, LaplacianType):
+    raise TypeError("laplacian_type must be a LaplacianType")
   d = rowsum if r is None else rowsum * r
   if laplacian_type == LaplacianType.Unnormalized:
     return d, r, None, -1.0, nat.EIG_SMALLEST

@@ -9,10 +9,10 @@ row block [row_begin, row_end) of every N x N matrix:
   3. blur statistics pass -> row maxima of the owned rows -> ALL-GATHER of N floats
      (the fused threshold/symmetrize rule needs m_i and m_j, SURVEY.md A.3);
   4. blur + threshold + symmetrize pass -> owned rows of Y as split fp16 planes;
-  5. Diffuse: S_block = Y_block * Y^T needs every row of Y: the peers' row blocks arrive by
-     asynchronous BROADCASTs (one per peer, issued up front on the communicator's stream) while
-     the tensor cores work through S_block[:, cols of peer p] = Y_block * Y_p^T in the order
-     the blocks land -- the own diagonal block first, which needs no traffic at all;
+  5. Diffuse: S = Y Y^T is symmetric, so rank g computes only S(g,g) and the blocks S(g, g+o),
+     o = 1..G/2: it fetches those peers' Y row blocks point-to-point (posted up front, landing
+     while the tensor cores work on the own diagonal block, which needs no traffic), and the
+     other half of its row block arrives as transposed copies of what the peers computed;
   6. row maxima / sums of S_block (RowWiseNormalize, Laplacian degree) are row-local.
 
 The orchestration below is backend-agnostic: `DeviceBackend` runs the CUDA kernels through the C
@@ -32,7 +32,15 @@ def _round_up(x: int, m: int) -> int:
 
 
 class ShardPlan:
-  """Row partition of an n x n problem over `world` ranks, with the blur halo of `radius`."""
+  """Row partition of an n x n problem over `world` ranks, with the blur halo of `radius`.
+
+  Block schedule of the symmetric product S = Y Y^T (G x G blocks of `block` rows): rank g
+  computes S(g, g) and S(g, g+o) for the offsets o = 1 .. G/2 (mod G), and receives the
+  remaining blocks S(g, g-o) = S(g-o, g)^T, o = 1 .. ceil(G/2)-1, transposed from the ranks that
+  computed them.  Odd G: every off-diagonal block pair is computed exactly once; even G: the
+  offset-G/2 pairs are computed on both sides (G/2 + 1/2 block products per rank instead of G/2).
+  Only the Y row blocks at the compute offsets are fetched.
+  """
 
   def __init__(self, n: int, world: int, rank: int, radius: int, align: int = 128):
     if world < 1 or not 0 <= rank < world:
@@ -58,9 +66,35 @@ class ShardPlan:
   def halo_rows(self) -> int:
     return self.halo_end - self.halo_begin
 
-  def peer_order(self) -> typing.List[int]:
-    """Own block first (no traffic), then the peers in broadcast (= arrival) order."""
-    return [self.rank] + [p for p in range(self.world) if p != self.rank]
+  def compute_peers(self) -> typing.List[int]:
+    """Ranks p != rank whose block S(rank, p) this rank computes (needs Y_p)."""
+    return [(self.rank + o) % self.world for o in range(1, self.world // 2 + 1)]
+
+  def mirror_sources(self) -> typing.List[int]:
+    """Ranks q whose computed S(q, rank) arrives here transposed as S(rank, q)."""
+    return [(self.rank - o) % self.world for o in range(1, (self.world + 1) // 2)]
+
+  def y_consumers(self) -> typing.List[int]:
+    """Ranks that compute against this rank's Y block (the inverse of compute_peers)."""
+    return [(self.rank - o) % self.world for o in range(1, self.world // 2 + 1)]
+
+  def mirror_targets(self) -> typing.List[int]:
+    """Ranks that receive one of this rank's computed blocks transposed."""
+    return [(self.rank + o) % self.world for o in range(1, (self.world + 1) // 2)]
+
+
+class _Once:
+  """A work handle whose wait() is idempotent (gloo hangs on a second wait of the same op)."""
+
+  def __init__(self, work, after=None):
+    self.work, self.done, self.after = work, False, after or []
+
+  def wait(self):
+    if not self.done:
+      self.work.wait()
+      for fn in self.after:
+        fn()
+      self.done = True
 
 
 def blur_radius(sigma: float) -> int:
@@ -92,11 +126,43 @@ class ShardedRefiner:
       raise NotImplementedError("sharded pipeline: RowMax thresholding only")
     self.sigma = float(options.gaussian_blur_sigma) if self.has_blur else 0.0
     self.sym_max = options.symmetrize_type == rf.SymmetrizeType.Max
+    self.trace = None              # set to [] to collect (label, backend.mark()) pairs
+
+  def _mark(self, label):
+    if self.trace is not None:
+      self.trace.append((label, self.backend.mark()))
+
+  def _p2p(self, sends, recvs):
+    """Post point-to-point transfers [(tensor, peer), ...]; returns one work handle per recv."""
+    d = self.dist
+    if not sends and not recvs:
+      return [], []
+    # gloo cannot send/recv device tensors: the single-GPU test configuration (two ranks sharing
+    # one GPU over gloo) stages them through host memory; NCCL moves them GPU to GPU.
+    staged = d.get_backend(self.group) == "gloo"
+    ops, landing = [], []
+    for t, peer in recvs:
+      if staged and t.is_cuda:
+        host = t.new_empty(t.shape, device="cpu")
+        landing.append([lambda t=t, host=host: t.copy_(host)])
+        ops.append(d.P2POp(d.irecv, host, peer, self.group))
+      else:
+        landing.append([])
+        ops.append(d.P2POp(d.irecv, t, peer, self.group))
+    for t, peer in sends:
+      ops.append(d.P2POp(d.isend, t.cpu() if (staged and t.is_cuda) else t, peer, self.group))
+    raw = d.batch_isend_irecv(ops)
+    if len(raw) == len(ops):                         # gloo: one work per op
+      works = [_Once(w, landing[i] if i < len(recvs) else None) for i, w in enumerate(raw)]
+      return works[:len(recvs)], works
+    works = [_Once(w) for w in raw]                  # NCCL: a single work for the whole group
+    return [works[-1]] * len(recvs), works
 
   def run(self, embeddings, world: int = 1, rank: int = 0):
     be, opt = self.backend, self.options
     n = int(embeddings.shape[0])
     plan = ShardPlan(n, world, rank, blur_radius(self.sigma))
+    self._mark("start")
     planes = be.normalize(embeddings)
     # affinity of the owned rows + halo; CropDiagonal values for exactly those rows
     a_ext, crop = be.affinity_block(planes, n, plan.halo_begin, plan.halo_rows, self.has_crop)
@@ -106,28 +172,53 @@ class ShardedRefiner:
                          bool(opt.thresholding_preserve_diagonal), m_full)
     if world > 1:
       self._all_gather_blocks(m_full, plan)
-    # owned rows of Y straight into the full-size planes (the peers' blocks land beside them)
+    self._mark("rowmax gathered")
+    # owned rows of Y straight into the full-size planes (the fetched peer blocks land beside them)
     y_full = be.new_planes(world * plan.block, n)
     be.thrsym_block(a_ext, n, plan, crop, self.sigma, m_full, opt, self.sym_max, y_full)
     del a_ext
-    works = []
+    self._mark("Y block done")
+
+    def yblk(p):
+      return [plane[p * plan.block:(p + 1) * plan.block] for plane in y_full]
+
+    recv_works, all_works = [], []
+    peers = plan.compute_peers() if world > 1 else []
+    be.reserve_comm_sms(world > 1)     # leave SMs to the send/recv kernels during the GEMMs
     if world > 1:
-      for p in range(world):                       # same order on every rank
-        lo = p * plan.block
-        for plane in y_full:
-          works.append((p, self.dist.broadcast(plane[lo:lo + plan.block], src=p,
-                                               group=self.group, async_op=True)))
+      recvs = [(t, p) for p in peers for t in yblk(p)]
+      sends = [(t, q) for q in plan.y_consumers() for t in yblk(rank)]
+      recv_works, all_works = self._p2p(sends, recvs)
     s_block = be.new_block(plan.rows, n)
-    for p in plan.peer_order():
-      if p != rank:
-        for q, w in works:
-          if q == p:
-            w.wait()                               # stream-ordered on CUDA, blocking on gloo
+    be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block)
+    self._mark("own block")
+    for idx, p in enumerate(peers):
+      for w in recv_works[idx * len(y_full):(idx + 1) * len(y_full)]:
+        w.wait()                                     # stream-ordered on CUDA, blocking on gloo
       lo, hi = plan.rows_of(p)
       be.gemm_block(y_full, plan.row_begin, plan.rows, lo, hi - lo, n, s_block)
-    for _, w in works:
+    for w in all_works:
       w.wait()
+    be.reserve_comm_sms(False)
+    self._mark("computed blocks")
+    if world > 1 and plan.mirror_targets():
+      outgoing = []
+      for p in plan.mirror_targets():                # S(rank, p) -> rank p as S(p, rank)
+        lo, hi = plan.rows_of(p)
+        outgoing.append((be.transposed_block(s_block, plan.rows, lo, hi - lo), p))
+      incoming = []
+      for q in plan.mirror_sources():
+        lo, hi = plan.rows_of(q)
+        incoming.append((be.new_dense(plan.rows, hi - lo), q))
+      recv_w, all_w = self._p2p(outgoing, incoming)
+      for w in all_w:
+        w.wait()
+      for buf, q in incoming:
+        lo, hi = plan.rows_of(q)
+        be.place_block(s_block, lo, hi - lo, buf)
+    self._mark("mirrored blocks")
     rowmax, rowsum = be.row_stats_block(s_block, plan.rows, n)
+    self._mark("row stats")
     return dict(plan=plan, s_block=s_block, rowmax=rowmax, rowsum=rowsum, y_planes=y_full)
 
   def _all_gather_blocks(self, full, plan):
@@ -144,6 +235,20 @@ class DeviceBackend:
     from . import device as dev
     self.eng, self.nat, self.dev = engine, nat, dev
     self.t = dev.torch()
+    # The N x N-scale buffers are allocated once and reused by every run(): at N = 131,072 they
+    # add up to >100 GB per GPU and re-allocating them costs ~1 s of cudaMalloc/cudaFree per step.
+    # (A result that must survive the next run() has to be cloned by the caller.)
+    self._buffers = {}
+
+  def _buffer(self, tag, shape, dtype):
+    key = (tag, tuple(shape), dtype)
+    buf = self._buffers.get(key)
+    if buf is None:
+      for k in [k for k in self._buffers if k[0] == tag]:
+        del self._buffers[k]                      # shape changed: drop the stale buffer first
+      buf = self.t.empty(shape, dtype=dtype, device=self.eng.device)
+      self._buffers[key] = buf
+    return buf
 
   def _p(self, t):
     return self.dev._ptr(t)
@@ -159,7 +264,10 @@ class DeviceBackend:
   def affinity_block(self, planes, n, row_begin, row_count, want_crop):
     eng, t = self.eng, self.t
     hi, lo, d = planes
-    a = t.empty((row_count, self.dev.round_up(n, 64)), dtype=t.float32, device=eng.device)
+    ld = self.dev.round_up(n, 64)
+    # the halo'd affinity block is dead before S_block is written: both live in one arena
+    arena = self._buffer("arena", (max(row_count, 1) + 2 * 64, ld), t.float32)
+    a = arena[:row_count]
     crop = t.zeros((n,), dtype=t.float32, device=eng.device) if want_crop else None
     eng.call("sc_affinity_cosine_block", eng.gemm_precision, self._p(hi), self._p(lo),
              hi.stride(0), n, d, row_begin, row_count, self._p(a), a.stride(0),
@@ -172,12 +280,15 @@ class DeviceBackend:
 
   def new_planes(self, rows, n):
     t, ld = self.t, self.dev.round_up(n, 64)
-    return (t.empty((rows, ld), dtype=t.float16, device=self.eng.device),
-            t.empty((rows, ld), dtype=t.float16, device=self.eng.device))
+    return (self._buffer("y_hi", (rows, ld), t.float16), self._buffer("y_lo", (rows, ld), t.float16))
 
   def new_block(self, rows, n):
-    return self.t.empty((rows, self.dev.round_up(n, 64)), dtype=self.t.float32,
-                        device=self.eng.device)
+    ld = self.dev.round_up(n, 64)
+    arena = next((b for k, b in self._buffers.items() if k[0] == "arena" and b.shape[1] == ld
+                  and b.shape[0] >= rows), None)
+    if arena is None:
+      arena = self._buffer("arena", (rows + 2 * 64, ld), self.t.float32)
+    return arena[:rows]
 
   def blur_rowmax_block(self, a_ext, n, plan, crop, sigma, zero_diag, m_full):
     eng = self.eng
@@ -208,6 +319,33 @@ class DeviceBackend:
              c(hi.data_ptr() + 2 * b_row * ld), c(lo.data_ptr() + 2 * b_row * ld), ld, b_rows, n,
              c(s_block.data_ptr() + 4 * b_row), s_block.stride(0), eng.stream)
 
+  comm_sms = 16
+
+  def reserve_comm_sms(self, on):
+    import ctypes
+    limit = (self.nat.load().sc_context_sm_count(self.eng.ctx) - self.comm_sms) if on else 0
+    self.nat.call("sc_context_set_gemm_sm_limit", self.eng.ctx, ctypes.c_int(limit))
+
+  def mark(self):
+    e = self.t.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+  def new_dense(self, rows, cols):
+    return self.t.empty((rows, cols), dtype=self.t.float32, device=self.eng.device)
+
+  def transposed_block(self, s_block, rows, col_begin, cols):
+    """Contiguous [cols, rows] copy of s_block[:, col_begin:col_begin+cols]^T."""
+    eng = self.eng
+    out = self.new_dense(cols, rows)
+    c = self.dev.ctypes.c_void_p
+    eng.call("sc_transpose", c(s_block.data_ptr() + 4 * col_begin), rows, cols,
+             s_block.stride(0), self._p(out), out.stride(0), eng.stream)
+    return out
+
+  def place_block(self, s_block, col_begin, cols, dense):
+    s_block[:, col_begin:col_begin + cols].copy_(dense)
+
   def row_stats_block(self, s_block, rows, n):
     eng, t = self.eng, self.t
     mx = t.empty((rows,), dtype=t.float64, device=eng.device)
@@ -215,6 +353,91 @@ class DeviceBackend:
     eng.call("sc_row_stats_block", self._p(s_block), rows, n, s_block.stride(0), self._p(mx),
              self._p(sm), eng.stream)
     return mx, sm
+
+
+def predict_sharded(clusterer, embeddings: np.ndarray, dist=None, group=None) -> np.ndarray:
+  """SpectralClusterer.predict() with every N x N matrix row-sharded over the ranks of `group`
+  (BASELINE.json configs[3]: N = 131,072 does not fit one GPU).  Every rank passes the same
+  embeddings and receives the same labels.
+
+  Refinement as in ShardedRefiner; row maxima / sums all-gathered (2 N doubles); eigensolve by the
+  sharded thick-restart Lanczos (each matvec streams the local row block and all-gathers N
+  doubles); eigengap and k-means replicated on the [N, k] eigenvectors."""
+  import ctypes
+  from . import _native as nat
+  from . import custom_distance_kmeans, device as dev, laplacian as lap, utils
+  from . import refinement as rf
+  t = dev.torch()
+  if not isinstance(embeddings, np.ndarray):
+    raise TypeError("embeddings must be a numpy array")
+  if len(embeddings.shape) != 2:
+    raise ValueError("embeddings must be 2-dimensional")
+  if clusterer.autotune or not clusterer.max_clusters:
+    raise NotImplementedError("predict_sharded: needs max_clusters and no AutoTune")
+  world = dist.get_world_size(group) if dist is not None else 1
+  rank = dist.get_rank(group) if dist is not None else 0
+  eng = dev.Engine.get()
+  be = DeviceBackend(eng)
+  x = np.ascontiguousarray(embeddings)
+  if x.dtype not in (np.float32, np.float64):
+    x = x.astype(np.float64)
+  x_dev = t.from_numpy(x).to(eng.device, non_blocking=True)
+  n = x.shape[0]
+  opt = clusterer.refinement_options
+  res = ShardedRefiner(be, opt, dist=dist if world > 1 else None, group=group).run(x_dev, world, rank)
+  plan = res["plan"]
+  length = world * plan.block
+
+  def gathered(local):
+    full = t.zeros((length,), dtype=t.float64, device=eng.device)
+    full[plan.row_begin:plan.row_end] = local
+    if world > 1:
+      dist.all_gather_into_tensor(full, full[rank * plan.block:(rank + 1) * plan.block].clone(),
+                                  group=group)
+    return full[:n].contiguous()
+
+  rowmax, rowsum = gathered(res["rowmax"]), gathered(res["rowsum"])
+  normalized = list(opt.refinement_sequence)[-1] == rf.RefinementName.RowWiseNormalize
+  r = (1.0 / rowmax) if normalized else None
+  delta, left, right, sign, which = lap.terms_from_row_sums(rowsum, r, clusterer.laplacian_type)
+  limit = min(n, clusterer.max_clusters + 1)
+  n_vectors = min(n, max(limit, clusterer.min_clusters or 0))
+  w = np.empty(limit, dtype=np.float64)
+  v = t.empty((n, n_vectors), dtype=t.float64, device=eng.device)
+  stats = np.zeros(4, dtype=np.int64)
+  y_full = t.zeros((length,), dtype=t.float64, device=eng.device)
+
+  def gather(_user):
+    try:
+      if world > 1:
+        dist.all_gather_into_tensor(y_full, y_full[rank * plan.block:(rank + 1) * plan.block].clone(),
+                                    group=group)
+      return 0
+    except Exception:                                  # never unwind through the C frame
+      return 1
+
+  callback = nat.GATHER_FN(gather)
+  s_block = res["s_block"]
+  eng.call("sc_eigh_extremal_sharded", dev._ptr(s_block), plan.rows, plan.row_begin, n,
+           s_block.stride(0), dev._ptr(delta), dev._ptr(left), dev._ptr(right), float(sign),
+           int(which), limit, n_vectors, 1e-9, 0, dev._ptr(y_full), callback, None,
+           w.ctypes.data_as(ctypes.c_void_p), dev._ptr(v), stats.ctypes.data_as(ctypes.c_void_p),
+           eng.stream)
+  descend = which == nat.EIG_LARGEST
+  if descend:
+    k, gap = utils.compute_number_of_clusters(
+        w, max_clusters=clusterer.max_clusters, stop_eigenvalue=clusterer.stop_eigenvalue,
+        eigengap_type=clusterer.eigengap_type, descend=True)
+  else:
+    if clusterer.eigengap_type == utils.EigenGapType.NormalizedDiff:
+      raise NotImplementedError("predict_sharded: NormalizedDiff on a Laplacian needs lambda_max")
+    k, gap = utils.compute_number_of_clusters(
+        w, max_clusters=clusterer.max_clusters, eigengap_type=clusterer.eigengap_type,
+        descend=False)
+  clusterer.last_details = dict(eigenvalues=w.copy(), n_clusters_raw=k, max_gap=gap,
+                                solver="lanczos-sharded x%d" % world,
+                                lanczos_stats=stats.tolist())
+  return clusterer._cluster_embeddings(eng, v, k)
 
 
 def parallel_autotune(evaluate: typing.Callable[[float], typing.Tuple[float, int]],

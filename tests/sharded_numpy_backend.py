@@ -91,5 +91,20 @@ class NumpyBackend:
     y = y_full[0].numpy()
     s_block[:, b_row:b_row + b_rows] = y[a_row:a_row + a_rows] @ y[b_row:b_row + b_rows].T
 
+  def reserve_comm_sms(self, on):
+    pass
+
+  def mark(self):
+    return None
+
+  def new_dense(self, rows, cols):
+    return torch.zeros((rows, cols), dtype=torch.float64)
+
+  def transposed_block(self, s_block, rows, col_begin, cols):
+    return torch.from_numpy(np.ascontiguousarray(s_block[:, col_begin:col_begin + cols].T))
+
+  def place_block(self, s_block, col_begin, cols, dense):
+    s_block[:, col_begin:col_begin + cols] = dense.numpy()
+
   def row_stats_block(self, s_block, rows, n):
     return s_block.max(axis=1), s_block.sum(axis=1)

@@ -124,3 +124,49 @@ def test_parallel_autotune_two_ranks_matches_reference_fixture():
   out = ctx.Queue()
   mp.spawn(_autotune_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
   assert out.get(timeout=30) == 1
+
+
+def _predict_worker(rank, world, port, use_nccl, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(rank if use_nccl else 0)
+  dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
+  import spectralcluster_b200 as scb
+  from spectralcluster_b200 import sharded
+  from oracle import spectral_oracle as orc
+  n = 3072
+  x, truth = orc.synthetic_dvectors(n, 128, 5, seed=4, return_labels=True)
+  ok = True
+  for lap in (None, scb.LaplacianType.GraphCut):
+    c = scb.SpectralClusterer(min_clusters=2, max_clusters=9, laplacian_type=lap,
+                              refinement_options=icassp_options(scb))
+    got = sharded.predict_sharded(c, x, dist=dist)
+    single = scb.SpectralClusterer(min_clusters=2, max_clusters=9, laplacian_type=lap,
+                                   refinement_options=icassp_options(scb))
+    ref = single.predict(x)
+    ok = ok and np.array_equal(scb.utils.enforce_ordered_labels(got),
+                               scb.utils.enforce_ordered_labels(ref))
+    ok = ok and np.array_equal(scb.utils.enforce_ordered_labels(got),
+                               scb.utils.enforce_ordered_labels(truth))
+    w1, w2 = c.last_details["eigenvalues"], single.last_details["eigenvalues"]
+    ok = ok and np.allclose(w1, w2[:len(w1)], rtol=1e-6, atol=1e-7 * np.abs(w2).max())
+  flags = torch.tensor([1 if ok else 0], device="cuda" if use_nccl else "cpu")
+  dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+  if rank == 0:
+    out.put(int(flags[0]))
+  dist.destroy_process_group()
+
+
+def test_predict_sharded_two_ranks_matches_single_gpu():
+  import torch
+  import torch.multiprocessing as mp
+  use_nccl = torch.cuda.device_count() >= 2
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  port = s.getsockname()[1]
+  s.close()
+  ctx = mp.get_context("spawn")
+  out = ctx.Queue()
+  mp.spawn(_predict_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
+  assert out.get(timeout=30) == 1

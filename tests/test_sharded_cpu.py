@@ -69,6 +69,16 @@ def test_sharded_refinement_two_ranks_gloo(n, sigma, crop, sym, keep_diag):
   assert out.get(timeout=10) == 1
 
 
+@pytest.mark.parametrize("world", [3, 4])
+def test_sharded_refinement_mirrored_blocks_gloo(world):
+  """3 and 4 ranks exercise the transposed-block exchange (odd and even block schedules)."""
+  ctx = mp.get_context("spawn")
+  out = ctx.Queue()
+  mp.spawn(_refine_worker, args=(world, free_port(), 900, 1, True, "max", False, out),
+           nprocs=world, join=True)
+  assert out.get(timeout=10) == 1
+
+
 def test_shard_plan():
   from spectralcluster_b200 import sharded
   p = sharded.ShardPlan(131072, 8, 3, 4)
@@ -76,7 +86,7 @@ def test_shard_plan():
                                                                          49148, 65540)
   p = sharded.ShardPlan(1000, 2, 1, 4)
   assert (p.block, p.row_begin, p.row_end, p.halo_begin, p.halo_end) == (512, 512, 1000, 508, 1000)
-  assert p.peer_order() == [1, 0]
+  assert p.compute_peers() == [0] and p.mirror_sources() == [] and p.y_consumers() == [0]
   covered = []
   for r in range(4):
     q = sharded.ShardPlan(70000, 4, r, 4)
@@ -85,6 +95,17 @@ def test_shard_plan():
   assert covered == list(range(70000))
   with pytest.raises(ValueError):
     sharded.ShardPlan(200, 4, 0, 4)
+  # block schedule: every (g, p) is either computed by g or mirrored from p, exactly as planned
+  for world in (1, 2, 3, 4, 5, 8):
+    plans = [sharded.ShardPlan(world * 256, world, r, 4) for r in range(world)]
+    for g, pl in enumerate(plans):
+      got = {g} | set(pl.compute_peers()) | set(pl.mirror_sources())
+      assert got == set(range(world))
+      assert not (set(pl.compute_peers()) & set(pl.mirror_sources()))
+      for q in pl.mirror_sources():
+        assert g in plans[q].compute_peers() and g in plans[q].mirror_targets()
+      for p2 in pl.compute_peers():
+        assert g in plans[p2].y_consumers()
 
 
 def _autotune_worker(rank, world, port, out):
