@@ -169,7 +169,7 @@ def run_reference(args, rank):
               "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 def run_sharded(args, eng, rank, world, dist):
@@ -219,7 +219,7 @@ def run_sharded(args, eng, rank, world, dist):
   if rank == 0:
     per = ms / args.steps
     gemm_ms = stages.get("sc_gemm_nt_planes", 0.0) / args.steps
-    print(json.dumps({
+    emit(({
         "metric": "embeddings/sec through the row-sharded refinement (affinity..Diffuse..row stats)",
         "value": n / (per / 1e3), "unit": "embeddings/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True, "scaling": "strong",
@@ -275,7 +275,7 @@ def run_sharded_predict(args, eng, rank, world, dist):
     correct = bool(np.array_equal(utils.enforce_ordered_labels(labels),
                                   utils.enforce_ordered_labels(truth)))
     per = sec / args.steps
-    print(json.dumps({
+    emit(({
         "metric": "embeddings/sec through predict() (row-sharded)", "value": n / per,
         "unit": "embeddings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -293,8 +293,39 @@ def run_sharded_predict(args, eng, rank, world, dist):
     dist.destroy_process_group()
 
 
+class StdoutGuard:
+  """Keeps stdout to the single JSON line: NCCL prints its version banner on fd 1 when the first
+  communicator is created, whatever NCCL_DEBUG says.  Everything written to fd 1 while the guard
+  is active goes to stderr; result() restores fd 1 and prints."""
+
+  def __init__(self):
+    sys.stdout.flush()
+    self.saved = os.dup(1)
+    os.dup2(2, 1)
+
+  def result(self, line: str):
+    sys.stdout.flush()
+    os.dup2(self.saved, 1)
+    os.close(self.saved)
+    sys.stdout.write(line + "\n")
+    sys.stdout.flush()
+
+
+GUARD = None
+
+
+def emit(obj):
+  line = json.dumps(obj)
+  if GUARD is not None:
+    GUARD.result(line)
+  else:
+    print(line)
+
+
 def main():
+  global GUARD
   args = parse()
+  GUARD = StdoutGuard()
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -431,7 +462,7 @@ def main():
   }
   if not args.no_cpu_baseline:
     line["cpu_baseline"] = cpu_baseline(args.cpu_sample_n, d, args.speakers)
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     dist.destroy_process_group()
 
