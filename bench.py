@@ -430,6 +430,13 @@ def main():
   flops = 2.0 * n * n * n           # algorithmic: full product Y Y^T
   achieved = flops / (diffuse_ms * 1e-3) / 1e12 if diffuse_ms > 0 else None
   hbm_peak = peaks.get("hbm_gbs") or 6650.0
+  # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same
+  # workload (profiles/traffic.json: {"diffuse_n<N>": bytes per launch}); null when absent.
+  traffic = None
+  try:
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("diffuse_n%d" % n)
+  except Exception:
+    pass
   line = {
       "metric": "embeddings/sec through predict()", "value": value, "unit": "embeddings/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -448,7 +455,7 @@ def main():
       "stage_ms": {k: v / args.steps for k, v in sorted(stages.items())},
       "roofline": {"kernel": "k_gemm_tcgen05 (Diffuse, Y Y^T)", "bound": "tensor",
                    "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                   "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                   "frac": (achieved / tensor_peak) if achieved else None, "traffic": traffic,
                    "peak_source": peak_note,
                    "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse; the "
                            "kernel issues 3x that in fp16 MMAs (hi*hi + hi*lo + lo*hi)"},

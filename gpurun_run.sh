@@ -1,17 +1,8 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-nvidia-smi -L | wc -l > gpurun_out/ngpu.txt
-run() { # nproc port out args...
-  np=$1; port=$2; out=$3; shift 3
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port $port bench.py --gpus $np "$@" > gpurun_out/$out.json 2> gpurun_out/$out.err
-}
-timeout 600 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout 500 --tb=short > gpurun_out/t_sharded8.log 2>&1
-run 8 29601 sp8_65k --steps 3 --warmup 2 --workload sharded-predict --size 65536
-run 4 29602 sp4_65k --steps 3 --warmup 2 --workload sharded-predict --size 65536
-run 2 29603 sp2_65k --steps 3 --warmup 2 --workload sharded-predict --size 65536
-run 8 29604 sp8_131k --steps 3 --warmup 2 --workload sharded-predict --size 131072
-run 4 29605 sp4_131k --steps 2 --warmup 2 --workload sharded-predict --size 131072
-run 8 29606 sr8_131k --steps 2 --warmup 2 --workload sharded-refine --size 131072
-run 8 29607 rep8 --steps 2 --warmup 3 --no-cpu-baseline
-tail -n 4 gpurun_out/t_sharded8.log
-for f in sp8_65k sp4_65k sp2_65k sp8_131k sp4_131k sr8_131k rep8; do echo "== $f"; tail -c 300 gpurun_out/$f.err | grep -v "^\*\|OMP_NUM\|^$"; head -c 260 gpurun_out/$f.json; echo; done
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --tb=short > gpurun_out/t_full.log 2>&1
+timeout 300 python tools/latency_small.py > gpurun_out/latency_small.txt 2>&1
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_gemm_tcgen05 -o gpurun_out/prof_gemm_65k python tools/profile_step.py --n 65536 --stop-after diffuse > gpurun_out/ncu_gemm65k.log 2>&1
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_65k_final.csv python tools/profile_step.py --n 65536 > gpurun_out/ncu_launch.log 2>&1
+tail -n 6 gpurun_out/t_full.log; cat gpurun_out/latency_small.txt | tail -4; tail -c 300 gpurun_out/bench_default.err; head -c 400 gpurun_out/bench_default.json

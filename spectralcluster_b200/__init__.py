@@ -1,34 +1,32 @@
 """spectralcluster_b200: the SpectralClusterer.predict() hot path of wq2012/SpectralCluster,
-built from scratch for NVIDIA B200 (sm_100a).  Import surface mirrors
-/root/reference/spectralcluster/__init__.py:14-43 for the names on that path."""
+built from scratch for NVIDIA B200 (sm_100a).
 
-from . import autotune
-from . import configs
-from . import custom_distance_kmeans
-from . import fallback_clusterer
-from . import laplacian
-from . import refinement
-from . import spectral_clusterer
-from . import utils
+The package-level names mirror the reference's import surface for that path
+(/root/reference/spectralcluster/__init__.py:14-43): users switch by changing the import.
+Names of reference components outside the hot path (constraints, multi-stage / naive clusterers)
+are intentionally absent -- see DESIGN.md section 1.
+"""
 
-AutoTune = autotune.AutoTune
-AutoTuneProxy = autotune.AutoTuneProxy
-
-FallbackOptions = fallback_clusterer.FallbackOptions
-SingleClusterCondition = fallback_clusterer.SingleClusterCondition
-FallbackClustererType = fallback_clusterer.FallbackClustererType
-
-LaplacianType = laplacian.LaplacianType
-
-RefinementName = refinement.RefinementName
-RefinementOptions = refinement.RefinementOptions
-ThresholdType = refinement.ThresholdType
-SymmetrizeType = refinement.SymmetrizeType
-
-SpectralClusterer = spectral_clusterer.SpectralClusterer
-
-EigenGapType = utils.EigenGapType
-
-ICASSP2018_REFINEMENT_SEQUENCE = configs.ICASSP2018_REFINEMENT_SEQUENCE
+from . import (autotune, configs, custom_distance_kmeans, fallback_clusterer, laplacian,
+               refinement, spectral_clusterer, utils)
 
 __version__ = "0.1.0"
+
+# public name -> defining submodule
+_EXPORTS = {
+    autotune: ("AutoTune", "AutoTuneProxy"),
+    fallback_clusterer: ("FallbackOptions", "SingleClusterCondition", "FallbackClustererType"),
+    laplacian: ("LaplacianType",),
+    refinement: ("RefinementName", "RefinementOptions", "ThresholdType", "SymmetrizeType"),
+    spectral_clusterer: ("SpectralClusterer",),
+    utils: ("EigenGapType",),
+    configs: ("ICASSP2018_REFINEMENT_SEQUENCE",),
+}
+for _module, _names in _EXPORTS.items():
+  for _name in _names:
+    globals()[_name] = getattr(_module, _name)
+
+__all__ = sorted(n for names in _EXPORTS.values() for n in names) + [
+    "autotune", "configs", "custom_distance_kmeans", "fallback_clusterer", "laplacian",
+    "refinement", "spectral_clusterer", "utils"]
+del _module, _names, _name

@@ -439,8 +439,18 @@ static int make_weights(double sigma, BlurWeights& bw, int& radius) {
   return 0;
 }
 
+static int check_outputs(const BlurArgs& g) {
+  SC_REQUIRE(!g.y || vec_ok_f32(g.y, g.ldy), "blur: `y` needs a 16-byte aligned base and ldy %% 4 == 0");
+  SC_REQUIRE(!g.out || vec_ok_f32(g.out, g.ldo), "blur: `out` needs a 16-byte aligned base and ldo %% 4 == 0");
+  SC_REQUIRE(!g.hi || (vec_ok_f16(g.hi, g.ldh) && vec_ok_f16(g.lo, g.ldh)),
+             "blur: the fp16 planes need 16-byte aligned bases and ldh %% 8 == 0");
+  SC_REQUIRE(!g.m || aligned16(g.m), "blur: the row-maximum vector needs a 16-byte aligned base");
+  return 0;
+}
+
 template <int EPI>
 static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStream_t st) {
+  if (int rc = check_outputs(g)) return rc;
   if (sigma <= 1e-15) {     // scipy: "if sigma > 1e-15 ... else output[...] = input[...]"
     const unsigned gy = (unsigned)std::min<int64_t>((g.n + 1023) / 1024, 64);
     k_noblur<EPI><<<dim3((unsigned)(g.row_end - g.row_begin), gy), 256, 0, st>>>(g); sc::launched();

@@ -45,6 +45,12 @@ void launched(int n = 1);   // bumps the process-wide kernel launch counter (sc_
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// fp32 matrix usable with 128-bit accesses: 16-byte aligned base, leading dimension % 4 == 0
+inline bool vec_ok_f32(const void* p, int64_t ld) { return aligned16(p) && (ld % 4) == 0; }
+// fp16 plane written with 128-bit stores / read by TMA: 16-byte aligned base, ld % 8 == 0
+inline bool vec_ok_f16(const void* p, int64_t ld) { return aligned16(p) && (ld % 8) == 0; }
+
 // RAII stream-ordered scratch.
 struct Scratch {
   void* p = nullptr;

@@ -332,6 +332,7 @@ extern "C" int sc_symmetrize(sc_context* ctx, const float* a, int64_t n, int64_t
 extern "C" int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64_t lda, void* hi,
                                void* lo, int64_t ldh, void* stream) {
   SC_REQUIRE(ctx && a && hi && lo && n > 0, "sc_split_planes: bad arguments");
+  SC_REQUIRE(vec_ok_f32(a, lda), "sc_split_planes: `a` needs a 16-byte aligned base and lda %% 4 == 0");
   const unsigned gx = (unsigned)((n + 1023) / 1024);
   k_split_planes<<<dim3((unsigned)n, gx), 256, 0, as_stream(stream)>>>(a, n, lda, (__half*)hi,
                                                                         (__half*)lo, ldh); sc::launched();
@@ -342,6 +343,7 @@ extern "C" int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64
 extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                             double* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && a && n > 0, "sc_row_stats: bad arguments");
+  SC_REQUIRE(vec_ok_f32(a, lda), "sc_row_stats: `a` needs a 16-byte aligned base and lda %% 4 == 0");
   k_row_stats<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, rowmax, rowsum); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
@@ -350,6 +352,7 @@ extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t 
 extern "C" int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows, int64_t cols,
                                   int64_t lda, double* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && a && rows > 0 && cols > 0, "sc_row_stats_block: bad arguments");
+  SC_REQUIRE(vec_ok_f32(a, lda), "sc_row_stats_block: `a` needs a 16-byte aligned base and lda %% 4 == 0");
   k_row_stats<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(a, cols, lda, rowmax, rowsum);
   sc::launched();
   SC_LAUNCH_CHECK();
@@ -380,6 +383,7 @@ extern "C" int sc_laplacian(sc_context* ctx, const float* w, int64_t n, int64_t 
   SC_REQUIRE(ctx && w && out && n > 0, "sc_laplacian: bad arguments");
   SC_REQUIRE(type >= SC_LAPLACIAN_AFFINITY && type <= SC_LAPLACIAN_GRAPHCUT,
              "Unsupported laplacian_type.");
+  SC_REQUIRE(vec_ok_f32(w, ldw), "sc_laplacian: `w` needs a 16-byte aligned base and ldw %% 4 == 0");
   cudaStream_t st = as_stream(stream);
   Scratch deg;
   SC_CUDA(deg.alloc(sizeof(double) * (size_t)n, st));

@@ -48,8 +48,8 @@ class Engine:
   # matrices smaller than this use the SIMT fp64-accumulate GEMM (a 128x256 tcgen05 tile would
   # be mostly padding); everything else goes through the tensor-core kernel.
   simt_below = 64
-  # dense (full-spectrum) eigensolver up to this N when only a few eigenpairs are needed
-  dense_eig_max = 2048
+  # force the dense (full-spectrum) eigensolver up to this N even when Lanczos would do (tests)
+  dense_eig_max = 0
 
   def __init__(self, device: int = 0):
     t = torch()

@@ -255,6 +255,24 @@ def test_lanczos_matches_dense(engine, kind):
   assert stats[0] > 0
 
 
+@pytest.mark.parametrize("which", [nat.EIG_LARGEST, nat.EIG_SMALLEST])
+def test_lanczos_thick_restart_on_dense_spectrum(engine, which):
+  """A random symmetric matrix has no gaps at the edge of its spectrum: the 64-vector basis is not
+  enough and the solver has to restart (several times) -- exercises k_combine / the arrowhead."""
+  n = 1500
+  rng = np.random.default_rng(1)
+  b = rng.standard_normal((n, n))
+  a = ((b + b.T) / 2).astype(np.float32).astype(np.float64)
+  w, v, stats = run_eigh(engine, a, None, None, None, 1.0, which, 11, 11, False)
+  ref = np.linalg.eigvalsh(a)
+  ref = ref[::-1][:11] if which == nat.EIG_LARGEST else ref[:11]
+  np.testing.assert_allclose(w, ref, rtol=0, atol=1e-8 * np.abs(ref).max())
+  assert stats[1] >= 1 and stats[2] == 11          # restarted, and all 11 pairs converged
+  resid = a @ v - v * w[None, :]
+  assert np.abs(resid).max() <= 1e-6 * np.abs(ref).max()
+  np.testing.assert_allclose(v.T @ v, np.eye(11), atol=1e-8)
+
+
 # ---------------------------------------------------------------- k-means
 @pytest.mark.parametrize("metric", ["cosine", "euclidean"])
 @pytest.mark.parametrize("n,k,seed", [(6, 2, 0), (450, 5, 1), (1000, 4, 2), (5000, 7, 3),
@@ -270,6 +288,18 @@ def test_kmeans_vs_oracle(metric, n, k, seed):
   want = orc.run_kmeans(e, k, metric, 300)
   np.testing.assert_array_equal(got, want)      # same seeds => same raw labels, not just up to order
   assert got.dtype == np.int64
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_kmeans_lonely_first_sample_quirk(metric):
+  """Sample 0 alone in its cluster: `np.where(...)[0].any()` is False for array([0]), so the
+  reference never updates that centroid (custom_distance_kmeans.py:137-138)."""
+  rng = np.random.default_rng(12)
+  e = np.vstack([[[9.0, -7.0, 8.0]], rng.standard_normal((150, 3)) * 0.2 + [1, 1, 0],
+                 rng.standard_normal((150, 3)) * 0.2 + [-1, 0.5, 1]])
+  got = scb.custom_distance_kmeans.run_kmeans(e, 3, metric, 300)
+  want = orc.run_kmeans(e, 3, metric, 300)
+  np.testing.assert_array_equal(got, want)
 
 
 def test_kmeans_errors():
