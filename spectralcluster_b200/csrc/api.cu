@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -62,6 +63,9 @@ extern "C" int sc_context_create(int device, sc_context** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   ctx->gemm_sm_limit = 0;
+  ctx->gemm_pace = nullptr;
+  if (!getenv("SCB_NO_GEMM_PACING") && cudaMalloc(&ctx->gemm_pace, sizeof(unsigned int)) != cudaSuccess)
+    ctx->gemm_pace = nullptr;
   // keep stream-ordered scratch inside the pool between calls (no trim at every sync)
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -73,6 +77,7 @@ extern "C" int sc_context_create(int device, sc_context** out) {
 }
 
 extern "C" int sc_context_destroy(sc_context* ctx) {
+  if (ctx && ctx->gemm_pace) cudaFree(ctx->gemm_pace);
   delete ctx;
   return 0;
 }

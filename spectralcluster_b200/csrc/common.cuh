@@ -15,6 +15,7 @@ struct sc_context {
   int sm_count;
   size_t smem_optin;
   int cc_major, cc_minor;
+  unsigned int* gemm_pace;   // device counter for the GEMM producers' pacing checkpoints (one stream at a time)
   int gemm_sm_limit;   // 0 = all SMs; otherwise the persistent GEMM leaves SMs to concurrent NCCL kernels
 };
 

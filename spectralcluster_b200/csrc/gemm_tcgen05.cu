@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace sc {
@@ -32,6 +33,8 @@ constexpr int UMMA_K = 16;
 constexpr int A_PLANE_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_PLANE_BYTES = BN * BK * 2;           // 32 KB
 constexpr int GROUP_M = 16;
+constexpr int PACE_KB = 64;       // K-blocks between pacing checkpoints of the producers
+constexpr int PACE_SPINS = 400;   // x 100 ns: bounded wait (a hint, never a dependency)
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;            // trap instead of hanging the GPU
@@ -202,7 +205,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ TileTable tab, int M, int N, int K,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
-               int diag_shift) {
+               int diag_shift, unsigned int* __restrict__ pace, int pace_kb) {
   constexpr int STAGES = SPLIT ? 2 : 4;
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
@@ -262,10 +265,32 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // Pacing: the CTAs of a wave share their A/B panels through L2 only while they stream K
+        // at the same position.  Left alone they drift apart (ncu, N=65,536: 2.9 TB of DRAM reads
+        // for 0.05 TB of operands, L2 hit rate 39 %), so every PACE_KB K-blocks each producer
+        // signs in on a global counter and waits -- bounded, it is only a hint -- until the
+        // whole grid has reached the same checkpoint.  64 K-blocks x ~1.1 MB per wave and K-block
+        // keep the live window (~70 MB) inside the 126 MB L2.
+        const int ck_per_tile = (num_kb + pace_kb - 1) / pace_kb;
+        unsigned int passed = 0;
+        for (int round = 0; round * (int)gridDim.x < num_tiles; ++round) {
+          const int tile = round * (int)gridDim.x + (int)blockIdx.x;
+          if (tile >= num_tiles) {            // no tile in the last round: keep the targets reachable
+            if (pace) atomicAdd(pace, (unsigned int)ck_per_tile);
+            continue;
+          }
           const TileCoord tc = tile_coord<SYM>(tile, tiles_m, tiles_n, tab);
           const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
+            if (pace && kb % pace_kb == 0) {
+              atomicAdd(pace, 1u);
+              ++passed;
+              const unsigned int target = passed * gridDim.x;
+              for (int spin = 0; spin < PACE_SPINS; ++spin) {
+                if (*reinterpret_cast<volatile unsigned int*>(pace) >= target) break;
+                __nanosleep(100);
+              }
+            }
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
             const uint32_t bar = smem_u32(&full_bar[stage]);
             const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
@@ -481,7 +506,18 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   int sms = ctx->sm_count;
   if (ctx->gemm_sm_limit > 0 && ctx->gemm_sm_limit < sms) sms = ctx->gemm_sm_limit;
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift); sc::launched();
+  unsigned int* pace = nullptr;
+  static int pace_kb = 0;
+  if (pace_kb == 0) {
+    const char* e = getenv("SCB_GEMM_PACE_KB");
+    pace_kb = (e && atoi(e) > 0) ? atoi(e) : PACE_KB;
+  }
+  if (ctx->gemm_pace && (K + BK - 1) / BK >= 2 * pace_kb && tiles > grid) {
+    pace = ctx->gemm_pace;
+    SC_CUDA(cudaMemsetAsync(pace, 0, sizeof(unsigned int), st));
+  }
+  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
+                                           pace, pace_kb); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Times sc_diffuse (tcgen05 GEMM, Y Y^T) for one N with CUDA events."""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from spectralcluster_b200 import device as dev
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=65536); ap.add_argument("--iters", type=int, default=3)
+a = ap.parse_args()
+eng = dev.Engine.get(0); n = a.n
+y = eng.matrix(n); y.uniform_(0.0, 1.0)
+hi, lo = eng.split_planes(y, n); del y
+for _ in range(1): s = eng.diffuse(n, hi=hi, lo=lo); del s
+torch.cuda.synchronize()
+st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+st.record()
+for _ in range(a.iters): s = eng.diffuse(n, hi=hi, lo=lo); del s
+en.record(); torch.cuda.synchronize()
+ms = st.elapsed_time(en) / a.iters
+print("N=%d pacing=%s diffuse %.1f ms  %.0f TFLOP/s algorithmic (2N^3)" % (
+    n, "off" if os.environ.get("SCB_NO_GEMM_PACING") else "on", ms, 2.0 * n ** 3 / ms / 1e9))
