@@ -34,12 +34,10 @@ def _round_up(x: int, m: int) -> int:
 class ShardPlan:
   """Row partition of an n x n problem over `world` ranks, with the blur halo of `radius`.
 
-  Block schedule of the symmetric product S = Y Y^T (G x G blocks of `block` rows): rank g
-  computes S(g, g) and S(g, g+o) for the offsets o = 1 .. G/2 (mod G), and receives the
-  remaining blocks S(g, g-o) = S(g-o, g)^T, o = 1 .. ceil(G/2)-1, transposed from the ranks that
-  computed them.  Odd G: every off-diagonal block pair is computed exactly once; even G: the
-  offset-G/2 pairs are computed on both sides (G/2 + 1/2 block products per rank instead of G/2).
-  Only the Y row blocks at the compute offsets are fetched.
+  Block schedule of the symmetric product S = Y Y^T (G x G blocks of `block` rows): every
+  off-diagonal block pair {S(a,b), S(b,a) = S(a,b)^T} is computed exactly once and mirrored to the
+  other owner as a transposed copy (compute_jobs / mirror_jobs): G/2 block products per rank,
+  diagonal block included.  Only the Y rows a rank multiplies against are fetched.
   """
 
   def __init__(self, n: int, world: int, rank: int, radius: int, align: int = 128):
@@ -66,21 +64,48 @@ class ShardPlan:
   def halo_rows(self) -> int:
     return self.halo_end - self.halo_begin
 
-  def compute_peers(self) -> typing.List[int]:
-    """Ranks p != rank whose block S(rank, p) this rank computes (needs Y_p)."""
-    return [(self.rank + o) % self.world for o in range(1, self.world // 2 + 1)]
+  def split_row(self, rank: int) -> int:
+    """Row (relative to the block) at which rank's block is halved for the offset-G/2 pairing."""
+    lo, hi = self.rows_of(rank)
+    return min(hi - lo, _round_up((hi - lo + 1) // 2, 128))
 
-  def mirror_sources(self) -> typing.List[int]:
-    """Ranks q whose computed S(q, rank) arrives here transposed as S(rank, q)."""
-    return [(self.rank - o) % self.world for o in range(1, (self.world + 1) // 2)]
+  def compute_jobs(self, rank: typing.Optional[int] = None):
+    """Off-diagonal products of `rank`: [(peer, (r0, r1), (c0, c1))] meaning
+    S(rank, peer)[r0:r1, c0:c1] = Y_rank[r0:r1] * Y_peer[c0:c1]^T, indices relative to the blocks.
 
-  def y_consumers(self) -> typing.List[int]:
-    """Ranks that compute against this rank's Y block (the inverse of compute_peers)."""
-    return [(self.rank - o) % self.world for o in range(1, self.world // 2 + 1)]
+    Rank g takes the whole blocks at offsets 1 .. ceil(G/2)-1.  For even G the offset-G/2 block
+    pair {a < b} is split between its two owners: a computes the top half of its rows against
+    all of b, b computes all of its rows against the bottom half of a's rows -- together they
+    cover S(a, b) once.  Everything else reaches a rank as a transposed copy (mirror_jobs)."""
+    g = self.rank if rank is None else rank
+    G = self.world
+    rows_g = self.rows_of(g)[1] - self.rows_of(g)[0]
+    jobs = []
+    for o in range(1, (G + 1) // 2):
+      p = (g + o) % G
+      jobs.append((p, (0, rows_g), (0, self.rows_of(p)[1] - self.rows_of(p)[0])))
+    if G % 2 == 0 and G > 1:
+      p = (g + G // 2) % G
+      rows_p = self.rows_of(p)[1] - self.rows_of(p)[0]
+      if g < p:
+        jobs.append((p, (0, self.split_row(g)), (0, rows_p)))
+      else:
+        jobs.append((p, (0, rows_g), (self.split_row(p), rows_p)))
+    return [j for j in jobs if j[1][1] > j[1][0] and j[2][1] > j[2][0]]
 
-  def mirror_targets(self) -> typing.List[int]:
-    """Ranks that receive one of this rank's computed blocks transposed."""
-    return [(self.rank + o) % self.world for o in range(1, (self.world + 1) // 2)]
+  def mirror_jobs(self):
+    """Blocks other ranks compute for this rank: [(source, (r0, r1), (c0, c1))] meaning source
+    sends S(source, rank)[r0:r1, c0:c1] transposed; it lands at my rows c0:c1, source's
+    columns r0:r1."""
+    out = []
+    for q in range(self.world):
+      if q != self.rank:
+        out += [(q, rr, cc) for p, rr, cc in self.compute_jobs(q) if p == self.rank]
+    return out
+
+  def y_requests(self):
+    """Y rows other ranks need from this rank: [(consumer, (c0, c1))]."""
+    return [(q, cc) for q, _, cc in self.mirror_jobs()]
 
 
 class _Once:
@@ -182,40 +207,36 @@ class ShardedRefiner:
     def yblk(p):
       return [plane[p * plan.block:(p + 1) * plan.block] for plane in y_full]
 
+    jobs = plan.compute_jobs() if world > 1 else []
     recv_works, all_works = [], []
-    peers = plan.compute_peers() if world > 1 else []
     be.reserve_comm_sms(world > 1)     # leave SMs to the send/recv kernels during the GEMMs
     if world > 1:
-      recvs = [(t, p) for p in peers for t in yblk(p)]
-      sends = [(t, q) for q in plan.y_consumers() for t in yblk(rank)]
+      recvs = [(t[c0:c1], p) for p, _, (c0, c1) in jobs for t in yblk(p)]
+      sends = [(t[c0:c1], q) for q, (c0, c1) in plan.y_requests() for t in yblk(rank)]
       recv_works, all_works = self._p2p(sends, recvs)
     s_block = be.new_block(plan.rows, n)
-    be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block)
+    be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block, 0)
     self._mark("own block")
-    for idx, p in enumerate(peers):
+    for idx, (p, (r0, r1), (c0, c1)) in enumerate(jobs):
       for w in recv_works[idx * len(y_full):(idx + 1) * len(y_full)]:
         w.wait()                                     # stream-ordered on CUDA, blocking on gloo
-      lo, hi = plan.rows_of(p)
-      be.gemm_block(y_full, plan.row_begin, plan.rows, lo, hi - lo, n, s_block)
+      lo = plan.rows_of(p)[0]
+      be.gemm_block(y_full, plan.row_begin + r0, r1 - r0, lo + c0, c1 - c0, n, s_block, r0)
     for w in all_works:
       w.wait()
     be.reserve_comm_sms(False)
     self._mark("computed blocks")
-    if world > 1 and plan.mirror_targets():
-      outgoing = []
-      for p in plan.mirror_targets():                # S(rank, p) -> rank p as S(p, rank)
-        lo, hi = plan.rows_of(p)
-        outgoing.append((be.transposed_block(s_block, plan.rows, lo, hi - lo), p))
-      incoming = []
-      for q in plan.mirror_sources():
-        lo, hi = plan.rows_of(q)
-        incoming.append((be.new_dense(plan.rows, hi - lo), q))
-      recv_w, all_w = self._p2p(outgoing, incoming)
+    if world > 1:
+      outgoing = []                                  # S(rank, p)[r0:r1, c0:c1]^T -> rank p
+      for p, (r0, r1), (c0, c1) in jobs:
+        lo = plan.rows_of(p)[0]
+        outgoing.append((be.transposed_block(s_block, r0, r1 - r0, lo + c0, c1 - c0), p))
+      incoming = [(be.new_dense(c1 - c0, r1 - r0), q) for q, (r0, r1), (c0, c1) in plan.mirror_jobs()]
+      _, all_w = self._p2p(outgoing, incoming)
       for w in all_w:
         w.wait()
-      for buf, q in incoming:
-        lo, hi = plan.rows_of(q)
-        be.place_block(s_block, lo, hi - lo, buf)
+      for (buf, q), (_, (r0, r1), (c0, c1)) in zip(incoming, plan.mirror_jobs()):
+        be.place_block(s_block, c0, plan.rows_of(q)[0] + r0, buf)
     self._mark("mirrored blocks")
     rowmax, rowsum = be.row_stats_block(s_block, plan.rows, n)
     self._mark("row stats")
@@ -309,7 +330,8 @@ class DeviceBackend:
              nat.SYMMETRIZE_MAX if sym_max else nat.SYMMETRIZE_AVERAGE, None, 0,
              c(hi.data_ptr() + off), c(lo.data_ptr() + off), hi.stride(0), eng.stream)
 
-  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block):
+  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block, s_row):
+    """s_block[s_row:s_row+a_rows, b_row:b_row+b_rows] = Y[a_row:+a_rows] Y[b_row:+b_rows]^T."""
     eng = self.eng
     hi, lo = y_full
     ld = hi.stride(0)
@@ -317,7 +339,8 @@ class DeviceBackend:
     eng.call("sc_gemm_nt_planes", eng.gemm_precision,
              c(hi.data_ptr() + 2 * a_row * ld), c(lo.data_ptr() + 2 * a_row * ld), ld, a_rows,
              c(hi.data_ptr() + 2 * b_row * ld), c(lo.data_ptr() + 2 * b_row * ld), ld, b_rows, n,
-             c(s_block.data_ptr() + 4 * b_row), s_block.stride(0), eng.stream)
+             c(s_block.data_ptr() + 4 * (s_row * s_block.stride(0) + b_row)), s_block.stride(0),
+             eng.stream)
 
   comm_sms = 16
 
@@ -334,17 +357,18 @@ class DeviceBackend:
   def new_dense(self, rows, cols):
     return self.t.empty((rows, cols), dtype=self.t.float32, device=self.eng.device)
 
-  def transposed_block(self, s_block, rows, col_begin, cols):
-    """Contiguous [cols, rows] copy of s_block[:, col_begin:col_begin+cols]^T."""
+  def transposed_block(self, s_block, row_begin, rows, col_begin, cols):
+    """Contiguous [cols, rows] copy of s_block[row_begin:+rows, col_begin:+cols]^T."""
     eng = self.eng
     out = self.new_dense(cols, rows)
     c = self.dev.ctypes.c_void_p
-    eng.call("sc_transpose", c(s_block.data_ptr() + 4 * col_begin), rows, cols,
-             s_block.stride(0), self._p(out), out.stride(0), eng.stream)
+    eng.call("sc_transpose", c(s_block.data_ptr() + 4 * (row_begin * s_block.stride(0) + col_begin)),
+             rows, cols, s_block.stride(0), self._p(out), out.stride(0), eng.stream)
     return out
 
-  def place_block(self, s_block, col_begin, cols, dense):
-    s_block[:, col_begin:col_begin + cols].copy_(dense)
+  def place_block(self, s_block, row_begin, col_begin, dense):
+    r, c = dense.shape
+    s_block[row_begin:row_begin + r, col_begin:col_begin + c].copy_(dense)
 
   def row_stats_block(self, s_block, rows, n):
     eng, t = self.eng, self.t

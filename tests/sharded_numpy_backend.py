@@ -87,9 +87,10 @@ class NumpyBackend:
         y[i - plan.row_begin, i] = 1.0
     y_full[0][plan.row_begin:plan.row_end] = torch.from_numpy(y)
 
-  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block):
+  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block, s_row):
     y = y_full[0].numpy()
-    s_block[:, b_row:b_row + b_rows] = y[a_row:a_row + a_rows] @ y[b_row:b_row + b_rows].T
+    s_block[s_row:s_row + a_rows, b_row:b_row + b_rows] = (
+        y[a_row:a_row + a_rows] @ y[b_row:b_row + b_rows].T)
 
   def reserve_comm_sms(self, on):
     pass
@@ -100,11 +101,13 @@ class NumpyBackend:
   def new_dense(self, rows, cols):
     return torch.zeros((rows, cols), dtype=torch.float64)
 
-  def transposed_block(self, s_block, rows, col_begin, cols):
-    return torch.from_numpy(np.ascontiguousarray(s_block[:, col_begin:col_begin + cols].T))
+  def transposed_block(self, s_block, row_begin, rows, col_begin, cols):
+    return torch.from_numpy(np.ascontiguousarray(
+        s_block[row_begin:row_begin + rows, col_begin:col_begin + cols].T))
 
-  def place_block(self, s_block, col_begin, cols, dense):
-    s_block[:, col_begin:col_begin + cols] = dense.numpy()
+  def place_block(self, s_block, row_begin, col_begin, dense):
+    r, c = dense.shape
+    s_block[row_begin:row_begin + r, col_begin:col_begin + c] = dense.numpy()
 
   def row_stats_block(self, s_block, rows, n):
     return s_block.max(axis=1), s_block.sum(axis=1)

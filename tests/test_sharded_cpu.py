@@ -86,7 +86,7 @@ def test_shard_plan():
                                                                          49148, 65540)
   p = sharded.ShardPlan(1000, 2, 1, 4)
   assert (p.block, p.row_begin, p.row_end, p.halo_begin, p.halo_end) == (512, 512, 1000, 508, 1000)
-  assert p.compute_peers() == [0] and p.mirror_sources() == [] and p.y_consumers() == [0]
+  assert p.compute_jobs() == [(0, (0, 488), (256, 512))] and p.mirror_jobs() == [(0, (0, 256), (0, 488))]
   covered = []
   for r in range(4):
     q = sharded.ShardPlan(70000, 4, r, 4)
@@ -95,17 +95,26 @@ def test_shard_plan():
   assert covered == list(range(70000))
   with pytest.raises(ValueError):
     sharded.ShardPlan(200, 4, 0, 4)
-  # block schedule: every (g, p) is either computed by g or mirrored from p, exactly as planned
-  for world in (1, 2, 3, 4, 5, 8):
-    plans = [sharded.ShardPlan(world * 256, world, r, 4) for r in range(world)]
+  # block schedule: every off-diagonal element of S is produced exactly once (computed or mirrored)
+  for world, n in ((1, 256), (2, 1000), (3, 900), (4, 1300), (5, 2100), (8, 8 * 384 - 50)):
+    plans = [sharded.ShardPlan(n, world, r, 4) for r in range(world)]
+    cover = np.zeros((n, n), dtype=np.int32)
     for g, pl in enumerate(plans):
-      got = {g} | set(pl.compute_peers()) | set(pl.mirror_sources())
-      assert got == set(range(world))
-      assert not (set(pl.compute_peers()) & set(pl.mirror_sources()))
-      for q in pl.mirror_sources():
-        assert g in plans[q].compute_peers() and g in plans[q].mirror_targets()
-      for p2 in pl.compute_peers():
-        assert g in plans[p2].y_consumers()
+      cover[pl.row_begin:pl.row_end, pl.row_begin:pl.row_end] += 1
+      for p2, (r0, r1), (c0, c1) in pl.compute_jobs():
+        lo = plans[p2].row_begin
+        cover[pl.row_begin + r0:pl.row_begin + r1, lo + c0:lo + c1] += 1
+      for q, (r0, r1), (c0, c1) in pl.mirror_jobs():
+        lo = plans[q].row_begin
+        cover[pl.row_begin + c0:pl.row_begin + c1, lo + r0:lo + r1] += 1
+      assert [q for q, _ in pl.y_requests()] == [q for q, _, _ in pl.mirror_jobs()]
+    assert cover.min() == 1 and cover.max() == 1, (world, n)
+  for world in (2, 3, 4, 8):                       # balance: ~G/2 block products per rank
+    n = world * 4096
+    plans = [sharded.ShardPlan(n, world, r, 4) for r in range(world)]
+    work = [pl.rows ** 2 / 2 + sum((r1 - r0) * (c1 - c0) for _, (r0, r1), (c0, c1) in pl.compute_jobs())
+            for pl in plans]
+    assert max(work) <= 1.02 * (n * n / 2 / world), (world, work)
 
 
 def _autotune_worker(rank, world, port, out):
