@@ -12,9 +12,7 @@ vectors, eigenvectors and the k-means state are fp64 vectors / N x k arrays.
 from __future__ import annotations
 
 import ctypes
-import math
 import os
-import time
 import typing
 
 import numpy as np
