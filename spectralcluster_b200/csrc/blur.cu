@@ -355,10 +355,136 @@ __device__ __forceinline__ void tile_compute(const BlurArgs& g, const float (&w)
   }
 }
 
-// One CTA per 32-row band, sweeping the column tiles with a 2-deep cp.async pipeline: the loads
-// of tile t+1 are in flight while tile t is filtered, so every resident CTA always has ~22 KB
-// outstanding (3 CTAs/SM) -- the first, load-then-compute version left HBM idle during the two
-// filter passes and ran latency-bound at ~28% of the roofline.
+// ---- fast path: interior, off-diagonal, full tiles (all but O(N) of the N^2/4096 tiles).
+// Everything that does not change from tile to tile inside a band is hoisted into FastCtx, and
+// nothing is bounds-checked: the general tile_fill / tile_compute above remain the fallback for
+// edge tiles, tiles that touch the diagonal (CropDiagonal patch, preserve_diagonal) and ragged
+// row blocks.
+template <int R>
+struct FastCtx {
+  static constexpr int FILL_ITERS = (TileGeom<R>::IH * (TileGeom<R>::IW / 4) + TTHREADS - 1) / TTHREADS;
+  int fill_smem[FILL_ITERS];   // float offset inside the tile buffer (-1: no copy this round)
+  int fill_gofs[FILL_ITERS];   // element offset from the tile's first source element
+  int v_in, v_mid;             // vertical pass: first input / output element (-1: idle)
+  int h_mid, h_c0;             // horizontal pass: first `mid` element (-1: idle), strip column
+  float cut_i;                 // m[i] * p of this thread's output row (EPI_THRSYM)
+  float* y_row;                // output row bases of this thread's row
+  __half* hi_row;
+  __half* lo_row;
+  float* out_row;
+};
+
+template <int R>
+__device__ __forceinline__ bool tile_is_fast(const BlurArgs& g, int64_t row0, int64_t col0) {
+  if (!tile_is_vec<R>(g, row0, col0)) return false;
+  if (col0 + TTW > g.n || row0 + TTH > g.row_end) return false;
+  // tiles whose halo'd footprint meets the diagonal take the general path
+  const int64_t lo = (row0 > col0 ? row0 : col0) - R;
+  const int64_t hi = ((row0 + TTH < col0 + TTW) ? row0 + TTH : col0 + TTW) + R;
+  return lo >= hi;
+}
+
+template <int R>
+__device__ __forceinline__ void fast_fill(const FastCtx<R>& c, const float* src, float* in) {
+#pragma unroll
+  for (int k = 0; k < FastCtx<R>::FILL_ITERS; ++k)
+    if (c.fill_smem[k] >= 0) cp_async16(in + c.fill_smem[k], src + c.fill_gofs[k]);
+}
+
+template <int R, int EPI>
+__device__ __forceinline__ void fast_compute(const BlurArgs& g, const FastCtx<R>& c,
+                                             const float (&w)[2 * R + 1], int64_t col0,
+                                             const float* in, float* mid, float& rmax) {
+  using G = TileGeom<R>;
+  if (c.v_in >= 0) {
+    float win[VSTRIP + 2 * R];
+#pragma unroll
+    for (int k = 0; k < VSTRIP + 2 * R; ++k) win[k] = in[c.v_in + k * G::IW];
+#pragma unroll
+    for (int o = 0; o < VSTRIP; ++o) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
+      mid[c.v_mid + o * G::MP] = acc;
+    }
+  }
+  __syncthreads();
+  if (c.h_mid >= 0) {
+    float win[HSTRIP + 2 * R];
+#pragma unroll
+    for (int k = 0; k < HSTRIP + 2 * R; ++k) win[k] = mid[c.h_mid + k];
+    float b[HSTRIP];
+#pragma unroll
+    for (int o = 0; o < HSTRIP; ++o) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k <= 2 * R; ++k) acc = fmaf(w[k], win[o + k], acc);
+      b[o] = acc;
+    }
+    const int64_t j0 = col0 + c.h_c0;
+    if (EPI == EPI_STATS) {
+      float v = rmax;
+#pragma unroll
+      for (int t = 0; t < HSTRIP; ++t) v = fmaxf(v, b[t]);
+      rmax = v;
+    } else if (EPI == EPI_STORE) {
+#pragma unroll
+      for (int q = 0; q < HSTRIP / 4; ++q)
+        *reinterpret_cast<float4*>(c.out_row + j0 + 4 * q) =
+            make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+      if (g.rowmax_out) {
+        float v = 0.0f;
+#pragma unroll
+        for (int t = 0; t < HSTRIP; ++t) v = fmaxf(v, b[t]);
+        atomic_max_nonneg(g.rowmax_out + (c.out_row - g.out) / g.ldo + g.out_row_base, v);
+      }
+    } else {
+      float y[HSTRIP];
+#pragma unroll
+      for (int q = 0; q < HSTRIP / 4; ++q) {
+        const float4 mq = *reinterpret_cast<const float4*>(g.m + j0 + 4 * q);   // warp-broadcast
+        const float mj[4] = {mq.x, mq.y, mq.z, mq.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float x = b[4 * q + t];
+          const float keep = g.binarize ? 1.0f : x;
+          const float small = x * g.mult;
+          const float t1 = (x < c.cut_i) ? small : keep;
+          const float t2 = (x < mj[t] * g.p) ? small : keep;
+          y[4 * q + t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
+        }
+      }
+      if (c.y_row) {
+#pragma unroll
+        for (int q = 0; q < HSTRIP / 4; ++q)
+          *reinterpret_cast<float4*>(c.y_row + j0 + 4 * q) =
+              make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      }
+      if (c.hi_row) {
+        uint32_t hw[HSTRIP / 2], lw[HSTRIP / 2];
+#pragma unroll
+        for (int q = 0; q < HSTRIP / 2; ++q) {
+          const __half2 h = __floats2half2_rn(y[2 * q], y[2 * q + 1]);
+          const float2 f = __half22float2(h);
+          const __half2 l = __floats2half2_rn(y[2 * q] - f.x, y[2 * q + 1] - f.y);
+          hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+          lw[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        uint4* hd = reinterpret_cast<uint4*>(c.hi_row + j0);
+        uint4* ld = reinterpret_cast<uint4*>(c.lo_row + j0);
+        hd[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        hd[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        ld[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        ld[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+      }
+    }
+  }
+}
+
+// One CTA per (32-row band, run of `tiles_per_cta` column tiles), 2-deep cp.async pipeline: the
+// loads of tile t+1 are in flight while tile t is filtered, so every resident CTA always has
+// ~22 KB outstanding (3 CTAs/SM) -- the first, load-then-compute version left HBM idle during
+// the two filter passes and ran latency-bound at ~28% of the roofline.
 //   EPI_STATS : row maxima of the blurred band, one register per thread, no atomics
 //   EPI_THRSYM/EPI_STORE : the band's output rows
 template <int R, int EPI>
@@ -374,25 +500,64 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
 #pragma unroll
   for (int k = 0; k <= 2 * R; ++k) w[k] = bw.w[k];
   float rmax = 0.0f;
+  const int tid = threadIdx.x;
   const int64_t row0 = g.row_begin + (int64_t)blockIdx.x * TTH;
   // blockIdx.y selects a run of `tiles_per_cta` column tiles of the band
   const int ntiles = (int)((g.n + TTW - 1) / TTW);
   const int tx0 = blockIdx.y * g.tiles_per_cta;
   const int ntx = min(ntiles, tx0 + g.tiles_per_cta);
-  tile_fill<R>(g, row0, (int64_t)tx0 * TTW, in0);
+
+  // ---- per-thread invariants of the band
+  FastCtx<R> c;
+#pragma unroll
+  for (int k = 0; k < FastCtx<R>::FILL_ITERS; ++k) {
+    const int idx = tid + k * TTHREADS;
+    const int r = idx / (G::IW / 4), q = idx - r * (G::IW / 4);
+    const bool on = idx < G::IH * (G::IW / 4);
+    c.fill_smem[k] = on ? r * G::IW + 4 * q : -1;
+    c.fill_gofs[k] = on ? (int)(r * g.lda) + 4 * q : 0;      // < 40 * lda: fits 32 bits
+  }
+  {
+    const bool von = tid < G::IW * (TTH / VSTRIP);
+    const int vc = tid % G::IW, vr0 = (tid / G::IW) * VSTRIP;
+    c.v_in = von ? vr0 * G::IW + vc : -1;
+    c.v_mid = vr0 * G::MP + vc;
+    const bool hon = tid < TTH * (TTW / HSTRIP);
+    const int hr = tid % TTH;
+    c.h_c0 = (tid / TTH) * HSTRIP;
+    c.h_mid = hon ? hr * G::MP + c.h_c0 : -1;
+    const int64_t i = row0 + hr;
+    const bool row_ok = hon && i < g.row_end;
+    const int64_t io = i - g.out_row_base;
+    c.cut_i = (EPI == EPI_THRSYM && row_ok) ? g.m[i] * g.p : 0.0f;
+    c.y_row = (row_ok && g.y) ? g.y + io * g.ldy : nullptr;
+    c.hi_row = (row_ok && g.hi) ? g.hi + io * g.ldh : nullptr;
+    c.lo_row = (row_ok && g.hi) ? g.lo + io * g.ldh : nullptr;
+    c.out_row = (row_ok && g.out) ? g.out + io * g.ldo : nullptr;
+  }
+  const float* band_src = g.a + (row0 - R - g.in_row_base) * g.lda - R;   // + col0 per tile
+
+  auto stage = [&](int tx, float* buf) {
+    const int64_t col0 = (int64_t)tx * TTW;
+    if (tile_is_fast<R>(g, row0, col0)) fast_fill<R>(c, band_src + col0, buf);
+    else tile_fill<R>(g, row0, col0, buf);
+  };
+  stage(tx0, in0);
   cp_async_commit();
   for (int tx = tx0; tx < ntx; ++tx) {
     float* cur = ((tx - tx0) & 1) ? in1 : in0;
     float* nxt = ((tx - tx0) & 1) ? in0 : in1;
     if (tx + 1 < ntx) {
-      tile_fill<R>(g, row0, (int64_t)(tx + 1) * TTW, nxt);   // `nxt` was last read two tiles ago
+      stage(tx + 1, nxt);                                     // `nxt` was last read two tiles ago
       cp_async_commit();
       cp_async_wait<1>();                                     // tile tx has landed
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();   // tile tx visible; everybody is out of the previous horizontal pass
-    tile_compute<R, EPI>(g, w, row0, (int64_t)tx * TTW, cur, mid, rmax);
+    const int64_t col0 = (int64_t)tx * TTW;
+    if (tile_is_fast<R>(g, row0, col0)) fast_compute<R, EPI>(g, c, w, col0, cur, mid, rmax);
+    else tile_compute<R, EPI>(g, w, row0, col0, cur, mid, rmax);
   }
   if (EPI == EPI_STATS) {
     if (threadIdx.x < TTH * (TTW / HSTRIP)) part[threadIdx.x / TTH][threadIdx.x % TTH] = rmax;
