@@ -8,18 +8,22 @@
 // which reproduces the fp32 product to ~2^-22 relative (the dropped lo*lo term is 2^-22) at the
 // fp16 tensor-pipe rate; SC_GEMM_SINGLE issues only the first (2^-11).
 //
-// Structure (one CTA per SM, persistent, 256 threads):
+// Structure (one CTA per SM, persistent, 384 threads = 3 warpgroups):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 (or 2) planes of a
-//            K block into a ring of stages, completion on an mbarrier (expect_tx)
+//            K block into a ring of stages, completion on an mbarrier (expect_tx); paced against
+//            the other CTAs' producers through a global checkpoint counter (see below)
 //   warp 1   MMA issuer: one lane issues tcgen05.mma M=128 N=256 K=16 from shared-memory
-//            descriptors into a TMEM accumulator (128 lanes x 256 fp32 columns), frees the
-//            stage with tcgen05.commit
-//   warp 2   TMEM allocator (512 columns = two accumulators, so the epilogue of tile t overlaps
-//            the main loop of tile t+1)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 (thread = accumulator row), fused (x+1)/2 and
-//            off-diagonal row maximum for the affinity, 128-bit global stores
-// Tiles are rasterised in groups of 16 M-blocks so that a wave of 148 CTAs shares
-// 16 A-panels and ~9 B-panels through L2.
+//            descriptors into one of two TMEM chain buffers (128 lanes x 256 fp32 columns each),
+//            frees the stage with tcgen05.commit; a chain is only 2 K-blocks long
+//   warp 2   TMEM allocator (512 columns)
+//   warps 4-11 epilogue (setmaxnreg 232): tcgen05.ld 32x32b.x32 of every finished chain, added
+//            round-to-nearest into a register-resident 128 x 256 fp32 tile (tcgen05 accumulates
+//            with truncation -- the two-level scheme keeps the bias below 1e-6); at the end of the
+//            tile: fused (x+1)/2 + off-diagonal row maximum (affinity), 128-bit stores, and the
+//            mirrored (transposed, coalesced) stores of the symmetric variant
+// Tiles are rasterised in groups of 16 M-blocks so that a wave of 148 CTAs shares 16 A-panels
+// and ~9 B-panels through L2; the symmetric variant (C = Y Y^T) computes only the tiles that touch
+// the upper triangle.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -35,7 +39,6 @@ constexpr int B_PLANE_BYTES = BN * BK * 2;           // 32 KB
 constexpr int GROUP_M = 16;
 constexpr int PACE_KB = 64;       // K-blocks between pacing checkpoints of the producers
 constexpr int PACE_SPINS = 400;   // x 100 ns: bounded wait (a hint, never a dependency)
-constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;            // trap instead of hanging the GPU
 
