@@ -110,6 +110,25 @@ class ClockSampler(threading.Thread):
             "reasons": reasons, "samples": len(self.rows)}
 
 
+def all_host_threads():
+  """Context manager: let NumPy/OpenBLAS and scikit-learn's OpenMP use every host core, even when
+  the launcher exported OMP_NUM_THREADS=1 (torchrun does)."""
+  import contextlib
+  try:
+    import threadpoolctl
+    return threadpoolctl.threadpool_limits(limits=os.cpu_count())
+  except Exception:
+    return contextlib.nullcontext()
+
+
+def host_threads():
+  try:
+    import threadpoolctl
+    return max((p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()), default=1)
+  except Exception:
+    return os.cpu_count()
+
+
 def cpu_baseline(sample_n, d, speakers, repeats=1):
   """Oracle predict() (NumPy/OpenBLAS, SciPy, scikit-learn; all host cores) on a bounded
   sample of the same workload.  eig is ~N^3, so the full N=65,536 is out of reach of the CPU
@@ -118,16 +137,13 @@ def cpu_baseline(sample_n, d, speakers, repeats=1):
   x = orc.synthetic_dvectors(sample_n, d, speakers, seed=0)
   opt = oracle_options()
   best = None
-  for _ in range(repeats):
-    t0 = time.perf_counter()
-    orc.predict(x, opt)
-    dt = time.perf_counter() - t0
-    best = dt if best is None else min(best, dt)
-  try:
-    import threadpoolctl
-    threads = max((p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()), default=1)
-  except Exception:
-    threads = os.cpu_count()
+  with all_host_threads():
+    for _ in range(repeats):
+      t0 = time.perf_counter()
+      orc.predict(x, opt)
+      dt = time.perf_counter() - t0
+      best = dt if best is None else min(best, dt)
+    threads = host_threads()
   return {"value": sample_n / best, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
           "sample": "oracle predict() on N=%d d=%d of the same generator (%.2f s); the CPU path "
                     "scales ~N^3 and cannot run N=65,536" % (sample_n, d, best),
@@ -142,18 +158,15 @@ def run_reference(args, rank):
   x = orc.synthetic_dvectors(args.cpu_sample_n, args.d, args.speakers, seed=0)
   opt = oracle_options()
   times = []
-  for i in range(total):
-    t0 = time.perf_counter()
-    orc.predict(x, opt)
-    times.append(time.perf_counter() - t0)
+  with all_host_threads():
+    for i in range(total):
+      t0 = time.perf_counter()
+      orc.predict(x, opt)
+      times.append(time.perf_counter() - t0)
+    threads = host_threads()
   timed = times[args.warmup:]
   sec = sum(timed) / len(timed)
   val = args.cpu_sample_n / sec
-  try:
-    import threadpoolctl
-    threads = max((p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()), default=1)
-  except Exception:
-    threads = os.cpu_count()
   line = {
       "impl": "reference", "metric": "embeddings/sec through predict()", "value": val,
       "unit": "embeddings/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -176,11 +189,10 @@ def run_sharded(args, eng, rank, world, dist):
   """configs[3]: one N x N problem, rows sharded over the ranks (spectralcluster_b200/sharded.py)."""
   import torch
   import spectralcluster_b200 as scb
-  from oracle import spectral_oracle as orc
   from spectralcluster_b200 import _native as nat
-  from spectralcluster_b200 import sharded
+  from spectralcluster_b200 import sharded, synthetic
   n, d = args.n, args.d
-  x = torch.from_numpy(orc.synthetic_dvectors(n, d, 8, seed=0).astype(np.float32)).to(eng.device)
+  x = torch.from_numpy(synthetic.speaker_turn_dvectors(n, d, 8, seed=0).astype(np.float32)).to(eng.device)
   opt = scb.RefinementOptions(gaussian_blur_sigma=1, p_percentile=0.95,
                               thresholding_soft_multiplier=0.01,
                               refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
@@ -240,11 +252,10 @@ def run_sharded(args, eng, rank, world, dist):
 def run_sharded_predict(args, eng, rank, world, dist):
   """One N x N problem end to end (predict) with every matrix row-sharded over the ranks."""
   import torch
-  from oracle import spectral_oracle as orc
   from spectralcluster_b200 import _native as nat
-  from spectralcluster_b200 import sharded
+  from spectralcluster_b200 import sharded, synthetic
   n, d = args.n, args.d
-  x, truth = orc.synthetic_dvectors(n, d, args.speakers, seed=0, return_labels=True)
+  x, truth = synthetic.speaker_turn_dvectors(n, d, args.speakers, seed=0, return_labels=True)
   x = x.astype(np.float32)
   clusterer = make_clusterer()
 
@@ -335,9 +346,9 @@ def main():
 
   import torch
   import torch.distributed as dist
-  from oracle import spectral_oracle as orc
   from spectralcluster_b200 import _native as nat
   from spectralcluster_b200 import device as dev
+  from spectralcluster_b200 import synthetic
 
   torch.cuda.set_device(local_rank)
   if world > 1:
@@ -353,7 +364,7 @@ def main():
     run_sharded_predict(args, eng, rank, world, dist)
     return
   # every rank clusters its own batch (different seed): weak scaling over independent units
-  x = orc.synthetic_dvectors(n, d, args.speakers, seed=rank).astype(np.float32)
+  x = synthetic.speaker_turn_dvectors(n, d, args.speakers, seed=rank).astype(np.float32)
   x_pinned = torch.from_numpy(x).pin_memory()
   clusterer = make_clusterer()
 

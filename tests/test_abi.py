@@ -110,3 +110,23 @@ def test_predict_input_validation_order():
     c.predict([[1.0, 2.0]])               # .shape is touched before the type check (A.4-1)
   with pytest.raises(ValueError):
     c.predict(np.zeros(3))
+
+
+def test_package_generator_equals_oracle_generator():
+  """bench.py feeds the GPU arm from spectralcluster_b200.synthetic and the CPU arm from the
+  oracle's copy: they must be the same inputs."""
+  from oracle import spectral_oracle as orc
+  from spectralcluster_b200 import synthetic
+  for n, d, k, seed in ((777, 32, 3, 0), (2048, 256, 6, 5)):
+    a, la = synthetic.speaker_turn_dvectors(n, d, k, seed=seed, return_labels=True)
+    b, lb = orc.synthetic_dvectors(n, d, k, seed=seed, return_labels=True)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(la, lb)
+
+
+def test_product_never_imports_the_oracle():
+  pkg = os.path.join(ROOT, "spectralcluster_b200")
+  for name in os.listdir(pkg):
+    if name.endswith(".py"):
+      text = open(os.path.join(pkg, name)).read()
+      assert "oracle" not in text.replace("the oracle's identical copy", ""), name

@@ -1,4 +1,6 @@
 #!/usr/bin/env python
+# Measurement script (not product code): times the B200 path NEXT TO the CPU oracle, like bench.py's
+# cpu_baseline leg.
 """BASELINE.json configs[0]: configs.icassp2018_clusterer.predict on N=1,000 d=128 (k=4): wall time
 of the B200 path and of the CPU oracle on the same box, medians of 5 after 2 warm-ups."""
 import os, sys, time

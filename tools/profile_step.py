@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from oracle import spectral_oracle as orc  # noqa: E402
+from spectralcluster_b200 import synthetic  # noqa: E402
 from spectralcluster_b200 import device as dev  # noqa: E402
 from spectralcluster_b200 import spectral_clusterer as sc_mod  # noqa: E402
 
@@ -27,7 +27,7 @@ ap.add_argument("--stop-after", default="")      # e.g. "diffuse": skip eigensol
 args = ap.parse_args()
 
 eng = dev.Engine.get(0)
-x = torch.from_numpy(orc.synthetic_dvectors(args.n, args.d, 6, seed=0).astype(np.float32)).to(eng.device)
+x = torch.from_numpy(synthetic.speaker_turn_dvectors(args.n, args.d, 6, seed=0).astype(np.float32)).to(eng.device)
 clusterer = bench.make_clusterer()
 
 
