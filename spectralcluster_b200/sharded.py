@@ -210,21 +210,23 @@ class ShardedRefiner:
     jobs = plan.compute_jobs() if world > 1 else []
     recv_works, all_works = [], []
     be.reserve_comm_sms(world > 1)     # leave SMs to the send/recv kernels during the GEMMs
-    if world > 1:
-      recvs = [(t[c0:c1], p) for p, _, (c0, c1) in jobs for t in yblk(p)]
-      sends = [(t[c0:c1], q) for q, (c0, c1) in plan.y_requests() for t in yblk(rank)]
-      recv_works, all_works = self._p2p(sends, recvs)
-    s_block = be.new_block(plan.rows, n)
-    be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block, 0)
-    self._mark("own block")
-    for idx, (p, (r0, r1), (c0, c1)) in enumerate(jobs):
-      for w in recv_works[idx * len(y_full):(idx + 1) * len(y_full)]:
-        w.wait()                                     # stream-ordered on CUDA, blocking on gloo
-      lo = plan.rows_of(p)[0]
-      be.gemm_block(y_full, plan.row_begin + r0, r1 - r0, lo + c0, c1 - c0, n, s_block, r0)
-    for w in all_works:
-      w.wait()
-    be.reserve_comm_sms(False)
+    try:
+      if world > 1:
+        recvs = [(t[c0:c1], p) for p, _, (c0, c1) in jobs for t in yblk(p)]
+        sends = [(t[c0:c1], q) for q, (c0, c1) in plan.y_requests() for t in yblk(rank)]
+        recv_works, all_works = self._p2p(sends, recvs)
+      s_block = be.new_block(plan.rows, n)
+      be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block, 0)
+      self._mark("own block")
+      for idx, (p, (r0, r1), (c0, c1)) in enumerate(jobs):
+        for w in recv_works[idx * len(y_full):(idx + 1) * len(y_full)]:
+          w.wait()                                   # stream-ordered on CUDA, blocking on gloo
+        lo = plan.rows_of(p)[0]
+        be.gemm_block(y_full, plan.row_begin + r0, r1 - r0, lo + c0, c1 - c0, n, s_block, r0)
+      for w in all_works:
+        w.wait()
+    finally:
+      be.reserve_comm_sms(False)
     self._mark("computed blocks")
     if world > 1:
       outgoing = []                                  # S(rank, p)[r0:r1, c0:c1]^T -> rank p
