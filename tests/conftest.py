@@ -13,6 +13,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+  # The C-ABI library is a build artefact (git-ignored): make sure it exists and is current
+  # before any test imports it (incremental: a no-op when the sources are unchanged).
+  from spectralcluster_b200 import build
+  build.build()
 
 
 def golden_names():
