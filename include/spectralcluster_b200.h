@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 1
+#define SC_ABI_VERSION 2
 
 /* enums mirror the reference's enum *names* (values are ours) */
 enum sc_threshold_type { SC_THRESHOLD_ROWMAX = 0, SC_THRESHOLD_PERCENTILE = 1 }; /* refinement.py:21-27 */
@@ -44,8 +44,9 @@ enum sc_gemm_engine {
   SC_GEMM_SIMT_F64ACC = 1 /* SIMT fp32 operands, fp64 accumulation (validation path, small N) */
 };
 enum sc_gemm_precision {
-  SC_GEMM_SPLIT3 = 0,    /* hi*hi + hi*lo + lo*hi : ~2^-22 relative */
-  SC_GEMM_SINGLE = 1     /* hi*hi only            : ~2^-11 relative */
+  SC_GEMM_SPLIT3 = 0,    /* hi*hi + hi*lo + lo*hi : ~2^-22 relative per product */
+  SC_GEMM_SINGLE = 1,    /* hi*hi only            : ~2^-11 relative per product */
+  SC_GEMM_SPLIT2 = 2     /* (hi+lo)*hi : B rounded to fp16, zero-mean 2^-12 per product */
 };
 enum sc_which_end { SC_EIG_LARGEST = 0, SC_EIG_SMALLEST = 1 };
 
@@ -128,10 +129,14 @@ int sc_blur_threshold_symmetrize(sc_context* ctx, const float* a, int64_t n, int
 int sc_split_planes(sc_context* ctx, const float* a, int64_t n, int64_t lda, void* hi, void* lo,
                     int64_t ldh, void* stream);
 
-/* Diffuse.refine (refinement.py:232-234): s = y y^T. */
+/* Diffuse.refine (refinement.py:232-234): s = y y^T.  rowmax (fp32) / rowsum (fp64), both or
+ * neither (tcgen05 engine only), receive max_j s[i,j] and sum_j s[i,j] from the GEMM epilogue: the
+ * reductions of the following RowWiseNormalize (refinement.py:243) and of the Laplacian degree
+ * (laplacian.py:41) without another pass over S.  The fused maximum assumes max_j s[i,j] >= 0,
+ * which holds for every y (s[i,i] = |y_i|^2). */
 int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y, int64_t ldy,
                const void* hi, const void* lo, int64_t ldh, int64_t n, float* s, int64_t lds,
-               void* stream);
+               float* rowmax, double* rowsum, void* stream);
 
 /* Row maxima and row sums (fp64) of an fp32 matrix: the reductions of
  * RowWiseNormalize (refinement.py:243) and of the degree (laplacian.py:41). */

@@ -45,7 +45,7 @@ PROTOTYPES = {
                                      c_i64, c_ptr],
     "sc_split_planes": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_diffuse": [c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64,
-                   c_ptr],
+                   c_ptr, c_ptr, c_ptr],
     "sc_row_stats": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "sc_row_normalize": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_laplacian": [c_ptr, c_ptr, c_i64, c_i64, c_int, c_dbl, c_ptr, c_i64, c_ptr],
@@ -77,7 +77,8 @@ THRESHOLD_ROWMAX, THRESHOLD_PERCENTILE = 0, 1
 SYMMETRIZE_MAX, SYMMETRIZE_AVERAGE = 0, 1
 LAPLACIAN_AFFINITY, LAPLACIAN_UNNORMALIZED, LAPLACIAN_RANDOMWALK, LAPLACIAN_GRAPHCUT = 0, 1, 2, 3
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
-GEMM_SPLIT3, GEMM_SINGLE = 0, 1
+GEMM_SPLIT3, GEMM_SINGLE, GEMM_SPLIT2 = 0, 1, 2
+ABI_VERSION = 2
 EIG_LARGEST, EIG_SMALLEST = 0, 1
 
 _lib = None
@@ -104,7 +105,7 @@ def load():
       fn.argtypes = args
       fn.restype = (ctypes.c_char_p if name == "sc_last_error" else
                     ctypes.c_longlong if name == "sc_launch_count" else ctypes.c_int)
-    if lib.sc_abi_version() != 1:
+    if lib.sc_abi_version() != ABI_VERSION:
       raise ImportError("spectralcluster_b200: ABI version mismatch")
     _lib = lib
     return lib

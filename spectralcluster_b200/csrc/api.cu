@@ -28,7 +28,8 @@ int gemm_nt_simt(int epi, const float* A, int64_t lda, const float* B, int64_t l
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, bool symmetric, int diag_shift, cudaStream_t st);
+                    float* rowmax_offdiag, bool symmetric, int diag_shift, float* stat_rowmax,
+                    double* stat_rowsum, cudaStream_t st);
 
 }  // namespace sc
 
@@ -105,23 +106,30 @@ extern "C" int sc_affinity_cosine(sc_context* ctx, int engine, int precision, co
              "sc_affinity_cosine: the tcgen05 engine needs the split fp16 planes");
   return gemm_nt_tcgen05(ctx, 1, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, d, a, lda,
-                         rowmax_offdiag, /*symmetric=*/false, /*diag_shift=*/0, as_stream(stream));
+                         rowmax_offdiag, /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr,
+                         as_stream(stream));
 }
 
 extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y,
                           int64_t ldy, const void* hi, const void* lo, int64_t ldh, int64_t n,
-                          float* s, int64_t lds, void* stream) {
+                          float* s, int64_t lds, float* rowmax, double* rowsum, void* stream) {
   SC_REQUIRE(ctx && s && n > 0, "sc_diffuse: bad arguments");
+  SC_REQUIRE((rowmax == nullptr) == (rowsum == nullptr), "sc_diffuse: rowmax/rowsum come together");
   if (engine == SC_GEMM_SIMT_F64ACC) {
     SC_REQUIRE(y, "sc_diffuse: the SIMT engine needs the fp32 operand");
+    SC_REQUIRE(!rowmax, "sc_diffuse: the SIMT engine has no fused row statistics");
     return gemm_nt_simt(0, y, ldy, y, ldy, n, n, n, s, lds, nullptr, as_stream(stream));
   }
   SC_REQUIRE(engine == SC_GEMM_TCGEN05, "sc_diffuse: unknown engine %d", engine);
   SC_REQUIRE(hi && (lo || precision == SC_GEMM_SINGLE),
              "sc_diffuse: the tcgen05 engine needs the split fp16 planes");
+  if (rowmax) {
+    SC_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(float) * n, as_stream(stream)));
+    SC_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * n, as_stream(stream)));
+  }
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, n, s, lds, nullptr,
-                         /*symmetric=*/true, /*diag_shift=*/0, as_stream(stream));
+                         /*symmetric=*/true, /*diag_shift=*/0, rowmax, rowsum, as_stream(stream));
 }
 
 // ---- row-block / general variants used by the row-sharded multi-GPU pipeline ----------------
@@ -136,7 +144,8 @@ extern "C" int sc_affinity_cosine_block(sc_context* ctx, int precision, const vo
   const __half* l = (const __half*)lo;
   return gemm_nt_tcgen05(ctx, 1, precision, h + row_begin * ldh, l ? l + row_begin * ldh : nullptr,
                          ldh, h, l, ldh, row_count, n, d, a_block, lda, rowmax_offdiag_block,
-                         /*symmetric=*/false, /*diag_shift=*/(int)row_begin, as_stream(stream));
+                         /*symmetric=*/false, /*diag_shift=*/(int)row_begin, nullptr, nullptr,
+                         as_stream(stream));
 }
 
 extern "C" int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi,
@@ -144,8 +153,9 @@ extern "C" int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_h
                                  const void* b_lo, int64_t ldb, int64_t n, int64_t k, float* c,
                                  int64_t ldc, void* stream) {
   SC_REQUIRE(ctx && a_hi && b_hi && c && m > 0 && n > 0 && k > 0, "sc_gemm_nt_planes: bad arguments");
-  SC_REQUIRE((a_lo && b_lo) || precision == SC_GEMM_SINGLE, "sc_gemm_nt_planes: lo planes missing");
+  SC_REQUIRE((a_lo && b_lo) || precision == SC_GEMM_SINGLE || (a_lo && precision == SC_GEMM_SPLIT2),
+             "sc_gemm_nt_planes: lo planes missing");
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)a_hi, (const __half*)a_lo, lda,
                          (const __half*)b_hi, (const __half*)b_lo, ldb, m, n, k, c, ldc, nullptr,
-                         /*symmetric=*/true, /*diag_shift=*/0, as_stream(stream));
+                         /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr, as_stream(stream));
 }

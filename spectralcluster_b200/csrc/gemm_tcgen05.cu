@@ -6,7 +6,10 @@
 // Operands are "split fp16 planes" (value = hi + lo).  Per 64-wide K block the MMA warp issues
 //     D += Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi          (tcgen05.mma kind::f16, fp32 accum)
 // which reproduces the fp32 product to ~2^-22 relative (the dropped lo*lo term is 2^-22) at the
-// fp16 tensor-pipe rate; SC_GEMM_SINGLE issues only the first (2^-11).
+// fp16 tensor-pipe rate.  SC_GEMM_SPLIT2 drops the B_lo plane (D += Alo*Bhi ; D += Ahi*Bhi: the
+// missing Ahi*Blo term is a zero-mean 2^-12 relative perturbation per product that averages down
+// with sqrt(K)); SC_GEMM_SINGLE issues only hi*hi (2^-11 on both sides).  profiles/ holds the
+// measured eigenvalue / label evidence for each mode.
 //
 // Structure (one CTA per SM, persistent, 384 threads = 3 warpgroups):
 //   warp 0   TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of the 4 (or 2) planes of a
@@ -200,7 +203,15 @@ constexpr int NUM_THREADS_V2 = 128 + NUM_EPI_WARPS * 32;   // 384
 //           (tcgen05.ld) and add it, round-to-nearest, into a register-resident 128 x 256 fp32
 //           tile (8 warps x 32 lanes x 128 registers), while the tensor core is already working
 //           on the next chain in the other TMEM buffer.
-template <bool SPLIT, int EPI, bool SYM>
+template <int PREC>
+struct StageGeom {
+  // planes of one K block in a stage: [A_hi][B_hi][A_lo (PREC>=2)][B_lo (PREC==3)]
+  static constexpr int BYTES = A_PLANE_BYTES * (PREC >= 2 ? 2 : 1) + B_PLANE_BYTES * (PREC == 3 ? 2 : 1);
+  static constexpr int STAGES = PREC == 3 ? 2 : (PREC == 2 ? 3 : 4);
+};
+constexpr int STORE_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;   // 32 KB: one 32x32 fp32 block per epilogue warp
+
+template <int PREC, int EPI, bool SYM>
 __global__ void __launch_bounds__(NUM_THREADS_V2, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
@@ -208,15 +219,18 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ TileTable tab, int M, int N, int K,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
-               int diag_shift, unsigned int* __restrict__ pace, int pace_kb) {
-  constexpr int STAGES = SPLIT ? 2 : 4;
-  constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
+               int diag_shift, unsigned int* __restrict__ pace, int pace_kb,
+               float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum) {
+  constexpr bool SPLIT = PREC >= 2;
+  constexpr int STAGES = StageGeom<PREC>::STAGES;
+  constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
-  constexpr int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? 1 : (SPLIT ? 2 : 4);
+  constexpr int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? 1 : (PREC == 1 ? 4 : 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* store_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STORE_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -232,10 +246,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
-    if (SPLIT) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
-    }
+    if (PREC >= 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    if (PREC == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -301,10 +313,9 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
             const int k0 = kb * BK;
             tma_load_2d(base, &map_a_hi, bar, k0, row_a);
             tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
-            if (SPLIT) {
-              tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
+            if (PREC >= 2) tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
+            if (PREC == 3)
               tma_load_2d(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_b_lo, bar, k0, row_b);
-            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -335,12 +346,18 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
             // The small cross products go first: tcgen05 truncates each accumulate to the
             // accumulator's current ulp, so terms added while the chain is still small cost
             // almost nothing; only the BK/16 hi*hi accumulates run at full magnitude.
-            if (SPLIT) {
+            if (PREC == 3) {
 #pragma unroll
               for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
                 umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, (in_chunk | kk) ? 1u : 0u);
                 umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            } else if (PREC == 2) {
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
+                umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, (in_chunk | kk) ? 1u : 0u);
               }
             }
 #pragma unroll
@@ -388,8 +405,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      // ---- write-out
-      const int64_t row = (int64_t)tc.m_blk * BM + quad * 32 + lane;
+      // ---- write-out.  Each thread holds one row x 128 columns; stored straight from registers
+      // that is 16 B per lane into 32 different rows.  Instead every 32x32 block goes through a
+      // per-warp staging buffer (float4 granules XOR-swizzled by row: conflict-free both ways) and
+      // leaves as 128-byte row segments, 4 rows per store instruction.
+      const int64_t row_base = (int64_t)tc.m_blk * BM + quad * 32;
+      const int64_t row = row_base + lane;
       const int64_t col0 = (int64_t)tc.n_blk * BN + half * 128;
       float rmax = 0.0f;
       if (EPI == TC_EPI_AFFINITY) {
@@ -398,32 +419,86 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
           sum[i] = (sum[i] + 1.0f) * 0.5f;                 // utils.py:39
           if (col0 + i != row + diag_shift && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
         }
+        if (row < M && rowmax_offdiag) atomic_max_nonneg(rowmax_offdiag + row, rmax);
       }
-      if (row < M) {
-        float* dst = C + row * ldc + col0;
+      if (EPI == TC_EPI_PLAIN && stat_rowmax) {
+        // fused RowWiseNormalize / degree reductions (refinement.py:243, laplacian.py:41): columns
+        // past N are zero-filled by TMA, so they change neither the sum nor a non-negative maximum
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, mx = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int64_t col = col0 + q * 4;
-          if (col + 3 < N) {
-            *reinterpret_cast<float4*>(dst + q * 4) =
-                make_float4(sum[q * 4], sum[q * 4 + 1], sum[q * 4 + 2], sum[q * 4 + 3]);
-          } else {
+        for (int i = 0; i < 128; i += 4) {
+          s0 += sum[i]; s1 += sum[i + 1]; s2 += sum[i + 2]; s3 += sum[i + 3];
+          mx = fmaxf(fmaxf(mx, fmaxf(sum[i], sum[i + 1])), fmaxf(sum[i + 2], sum[i + 3]));
+        }
+        if (row < M) {
+          atomic_max_nonneg(stat_rowmax + row, mx);
+          atomicAdd(stat_rowsum + row, (double)((s0 + s1) + (s2 + s3)));
+        }
+      }
+      {
+        float* stg = store_stage + (warp - 4) * 1024;
+        const int sr = lane >> 3, sq = lane & 7;             // store phase: row sr of 4, granule sq
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (col + t < N) dst[q * 4 + t] = sum[q * 4 + t];
+        for (int c = 0; c < 4; ++c) {
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                make_float4(sum[c * 32 + 4 * q], sum[c * 32 + 4 * q + 1], sum[c * 32 + 4 * q + 2],
+                            sum[c * 32 + 4 * q + 3]);
+          __syncwarp();
+          const int64_t col = col0 + c * 32 + sq * 4;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = rr * 4 + sr;
+            const float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((sq ^ (r & 7)) << 2));
+            if (row_base + r < M) {
+              float* dst = C + (row_base + r) * ldc + col;
+              if (col + 3 < N) {
+                *reinterpret_cast<float4*>(dst) = v;
+              } else {
+                if (col < N) dst[0] = v.x;
+                if (col + 1 < N) dst[1] = v.y;
+                if (col + 2 < N) dst[2] = v.z;
+              }
+            }
           }
         }
-        if (EPI == TC_EPI_AFFINITY && rowmax_offdiag) atomic_max_nonneg(rowmax_offdiag + row, rmax);
       }
       if (SYM) {
         // mirror into the tiles that were skipped: target (col, row) lies in tile
         // (col/128, row/256), which is skipped iff col/128 >= 2 (row/256) + 2.  col0 is a
         // multiple of 128, so the decision is uniform over this thread's 128 columns.
-        const bool mirror = (col0 / BM) >= 2 * (row / BN) + 2;
-        if (mirror && row < M) {
+        const bool mirror = (col0 / BM) >= 2 * (row_base / BN) + 2;
+        if (mirror) {
+          if (row < M) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (col0 + i < N) C[(col0 + i) * ldc + row] = sum[i];   // lanes -> consecutive rows
+            for (int i = 0; i < 128; ++i)
+              if (col0 + i < N) C[(col0 + i) * ldc + row] = sum[i];   // lanes -> consecutive rows
+          }
+          // the mirrored elements belong to rows col0 .. col0+127 of C: their reductions run
+          // across the lanes (rows >= M hold zeros / 0.5 and are masked)
+          if (EPI == TC_EPI_AFFINITY && rowmax_offdiag) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i) {
+              const float v = warp_max(row < M ? sum[i] : 0.0f);     // never on the diagonal
+              if (lane == 0 && col0 + i < N) atomic_max_nonneg(rowmax_offdiag + col0 + i, v);
+            }
+          }
+          if (EPI == TC_EPI_PLAIN && stat_rowmax) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i) {
+              const float x = row < M ? sum[i] : 0.0f;
+              const float mx = warp_max(x);
+              float sm = x;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+              if (lane == 0 && col0 + i < N) {
+                atomic_max_nonneg(stat_rowmax + col0 + i, mx);
+                atomicAdd(stat_rowsum + col0 + i, (double)sm);
+              }
+            }
+          }
         }
       }
     }
@@ -487,15 +562,17 @@ static void build_tile_table(TileTable& tab, int tiles_m, int tiles_n) {
   tab.num_tiles = total;
 }
 
-template <bool SPLIT, int EPI, bool SYM>
+template <int PREC, int EPI, bool SYM>
 static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
                   const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
-                  int64_t ldc, float* rowmax, int diag_shift, cudaStream_t st) {
-  constexpr int STAGES = SPLIT ? 2 : 4;
-  constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_PLANE_BYTES + B_PLANE_BYTES);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+                  int64_t ldc, float* rowmax, int diag_shift, float* stat_rowmax,
+                  double* stat_rowsum, cudaStream_t st) {
+  constexpr int STAGES = StageGeom<PREC>::STAGES;
+  constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align*/ +
+                      192 /*barriers*/;
   SC_REQUIRE(smem <= ctx->smem_optin, "tcgen05 GEMM needs %zu B of shared memory", smem);
-  auto kern = k_gemm_tcgen05<SPLIT, EPI, SYM>;
+  auto kern = k_gemm_tcgen05<PREC, EPI, SYM>;
   SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   TileTable tab = {};
@@ -520,7 +597,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     SC_CUDA(cudaMemsetAsync(pace, 0, sizeof(unsigned int), st));
   }
   kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
-                                           pace, pace_kb); sc::launched();
+                                           pace, pace_kb, stat_rowmax, stat_rowsum); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -528,35 +605,47 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
-                    float* rowmax_offdiag, bool symmetric, int diag_shift, cudaStream_t st) {
+                    float* rowmax_offdiag, bool symmetric, int diag_shift, float* stat_rowmax,
+                    double* stat_rowsum, cudaStream_t st) {
   SC_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31),
              "tcgen05 GEMM: bad shape");
   SC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0,
              "tcgen05 GEMM: C needs a 16-byte aligned base and ldc %% 4 == 0");
-  const bool split = (precision == SC_GEMM_SPLIT3);
+  SC_REQUIRE(precision == SC_GEMM_SPLIT3 || precision == SC_GEMM_SPLIT2 ||
+             precision == SC_GEMM_SINGLE, "tcgen05 GEMM: unknown precision %d", precision);
+  SC_REQUIRE((stat_rowmax == nullptr) == (stat_rowsum == nullptr),
+             "tcgen05 GEMM: the row statistics come together");
+  const int prec = precision == SC_GEMM_SPLIT3 ? 3 : (precision == SC_GEMM_SPLIT2 ? 2 : 1);
   CUtensorMap ah, al, bh, bl;
   if (int r = make_plane_map(&ah, a_hi, M, K, lda, BM)) return r;
   if (int r = make_plane_map(&bh, b_hi, N, K, ldb, BN)) return r;
-  if (split) {
+  al = ah;
+  bl = bh;
+  if (prec >= 2) {
+    SC_REQUIRE(a_lo, "tcgen05 GEMM: the lo plane of A is missing");
     if (int r = make_plane_map(&al, a_lo, M, K, lda, BM)) return r;
+  }
+  if (prec == 3) {
+    SC_REQUIRE(b_lo, "tcgen05 GEMM: the lo plane of B is missing");
     if (int r = make_plane_map(&bl, b_lo, N, K, ldb, BN)) return r;
-  } else {
-    al = ah;
-    bl = bh;
   }
   const int m = (int)M, n = (int)N, k = (int)K;
   // C = Y Y^T is symmetric when both operands are the same matrix: compute the upper tiles only
   const bool sym = symmetric && a_hi == b_hi && a_lo == b_lo && M == N && lda == ldb;
-#define SC_TC_LAUNCH(SP, EP, SY) \
-  return launch<SP, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, diag_shift, st)
-  if (split) {
-    if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(true, TC_EPI_AFFINITY, true); SC_TC_LAUNCH(true, TC_EPI_AFFINITY, false); }
-    if (sym) SC_TC_LAUNCH(true, TC_EPI_PLAIN, true);
-    SC_TC_LAUNCH(true, TC_EPI_PLAIN, false);
-  }
-  if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(false, TC_EPI_AFFINITY, true); SC_TC_LAUNCH(false, TC_EPI_AFFINITY, false); }
-  if (sym) SC_TC_LAUNCH(false, TC_EPI_PLAIN, true);
-  SC_TC_LAUNCH(false, TC_EPI_PLAIN, false);
+#define SC_TC_LAUNCH(PR, EP, SY)                                                              \
+  return launch<PR, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, diag_shift, \
+                            stat_rowmax, stat_rowsum, st)
+#define SC_TC_PREC(PR)                                                                        \
+  do {                                                                                        \
+    if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(PR, TC_EPI_AFFINITY, true);           \
+                                  SC_TC_LAUNCH(PR, TC_EPI_AFFINITY, false); }                 \
+    if (sym) SC_TC_LAUNCH(PR, TC_EPI_PLAIN, true);                                            \
+    SC_TC_LAUNCH(PR, TC_EPI_PLAIN, false);                                                    \
+  } while (0)
+  if (prec == 3) SC_TC_PREC(3);
+  if (prec == 2) SC_TC_PREC(2);
+  SC_TC_PREC(1);
+#undef SC_TC_PREC
 #undef SC_TC_LAUNCH
 }
 

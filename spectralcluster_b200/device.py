@@ -21,6 +21,10 @@ from . import _native as nat
 
 _torch = None
 
+# MMAs per product of the Diffuse GEMM; the evidence for the default is in
+# profiles/r02_diffuse_precision.md (eigenvalue error, label equality per scheme).
+DEFAULT_DIFFUSE_PRECISION = "split3"
+
 
 def torch():
   global _torch
@@ -57,7 +61,12 @@ class Engine:
     self.device_index = device
     self.device = t.device("cuda", device)
     self.ctx = nat.context(device)
-    self.gemm_precision = nat.GEMM_SPLIT3
+    self.gemm_precision = nat.GEMM_SPLIT3       # affinity: its entries feed a threshold
+    # Diffuse inside predict() (K = N): MMAs per product, SCB_DIFFUSE_PRECISION = split3 | split2
+    # | single.  The operator-level API (refinement.Diffuse) always uses split3.
+    self.diffuse_precision = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2,
+                              "single": nat.GEMM_SINGLE}[
+                                  os.environ.get("SCB_DIFFUSE_PRECISION", DEFAULT_DIFFUSE_PRECISION)]
     self.profile = None
 
   @classmethod
@@ -206,19 +215,26 @@ class Engine:
               self.stream)
     return hi, lo
 
-  def diffuse(self, n, y=None, hi=None, lo=None):
+  def diffuse(self, n, y=None, hi=None, lo=None, want_stats=False, precision=None):
+    """S = Y Y^T.  With want_stats (tcgen05 engine) also returns (rowmax fp32, rowsum fp64) of S
+    from the GEMM epilogue; otherwise (None, None).  `precision` defaults to the fp32-accurate
+    three-MMA split (the operator-level API); predict() passes `diffuse_precision`."""
+    t = torch()
+    precision = self.gemm_precision if precision is None else precision
     engine = self.gemm_engine(n)
     s = self.matrix(n)
     if engine == nat.GEMM_SIMT:
       assert y is not None
-      self.call("sc_diffuse", engine, self.gemm_precision, _ptr(y), y.stride(0), None, None, 0, n,
-                _ptr(s), s.stride(0), self.stream)
-    else:
-      if hi is None:
-        hi, lo = self.split_planes(y, n)
-      self.call("sc_diffuse", engine, self.gemm_precision, None, 0, _ptr(hi), _ptr(lo),
-                hi.stride(0), n, _ptr(s), s.stride(0), self.stream)
-    return s
+      self.call("sc_diffuse", engine, precision, _ptr(y), y.stride(0), None, None, 0,
+                n, _ptr(s), s.stride(0), None, None, self.stream)
+      return s, None, None
+    if hi is None:
+      hi, lo = self.split_planes(y, n)
+    mx = self.vector(n, t.float32) if want_stats else None
+    sm = self.vector(n, t.float64) if want_stats else None
+    self.call("sc_diffuse", engine, precision, None, 0, _ptr(hi), _ptr(lo),
+              hi.stride(0), n, _ptr(s), s.stride(0), _ptr(mx), _ptr(sm), self.stream)
+    return s, mx, sm
 
   def row_stats(self, a, n, want_max=True, want_sum=True):
     mx = self.vector(n) if want_max else None
@@ -282,14 +298,16 @@ class Refined:
   the matrix is diag(row_scale) * S with S fp32 on the device (`row_scale` None = ones).
   `symmetric` tells whether S is symmetric (up to rounding)."""
 
-  def __init__(self, s, n, symmetric, row_scale=None):
+  def __init__(self, s, n, symmetric, row_scale=None, rowsum=None):
     self.s = s
     self.n = n
     self.symmetric = symmetric
     self.row_scale = row_scale
+    self.rowsum = rowsum      # fp64 row sums of S when the Diffuse epilogue produced them
 
 
-def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetric=True) -> Refined:
+def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetric=True,
+                   diffuse_precision=None) -> Refined:
   """Apply options.refinement_sequence to the device affinity `a`.
 
   Fusions (all exact restatements):
@@ -307,6 +325,7 @@ def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetri
   planes = None          # (hi, lo) of `cur` when available
   cur_is_planes_only = False
   row_scale = None
+  stats = None           # (rowmax fp32, rowsum fp64) of `cur` straight from the Diffuse epilogue
   i = 0
   while i < len(names):
     name = names[i]
@@ -354,20 +373,31 @@ def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetri
     if name == RN.Diffuse:
       if row_scale is not None:
         cur, row_scale = _materialise_scale(eng, cur, n, row_scale), None
+      # the row reductions of a closing RowWiseNormalize / of the Laplacian degree come out of the
+      # GEMM epilogue when Diffuse is the last matrix-valued operator of the sequence
+      tail = names[i + 1:]
+      fuse_stats = (tail in ([], [RN.RowWiseNormalize]) and
+                    eng.gemm_engine(n) == nat.GEMM_TCGEN05)
       if planes is not None:
-        cur = eng.diffuse(n, hi=planes[0], lo=planes[1])
+        cur, mx, sm = eng.diffuse(n, hi=planes[0], lo=planes[1], want_stats=fuse_stats,
+                                  precision=diffuse_precision)
       else:
-        cur = eng.diffuse(n, y=cur)
+        cur, mx, sm = eng.diffuse(n, y=cur, want_stats=fuse_stats, precision=diffuse_precision)
+      stats = (mx, sm) if mx is not None else None
       planes, cur_is_planes_only, sym = None, False, True
       i += 1
       continue
     if cur_is_planes_only:
       raise AssertionError("internal: planes-only matrix consumed by a non-GEMM operator")
     if name == RN.RowWiseNormalize and i == len(names) - 1 and row_scale is None:
-      mx, _ = eng.row_stats(cur, n, want_max=True, want_sum=False)
+      if stats is not None:
+        mx = stats[0].double()
+      else:
+        mx, _ = eng.row_stats(cur, n, want_max=True, want_sum=False)
       row_scale = 1.0 / mx
       i += 1
       continue
+    stats = None
     if row_scale is not None:
       cur, row_scale = _materialise_scale(eng, cur, n, row_scale), None
       sym = False
@@ -398,7 +428,7 @@ def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetri
     else:
       raise ValueError("Unknown refinement operation: {}".format(name))
     i += 1
-  return Refined(cur, n, sym, row_scale)
+  return Refined(cur, n, sym, row_scale, stats[1] if stats is not None else None)
 
 
 def _materialise_scale(eng: Engine, s, n: int, row_scale):

@@ -61,7 +61,9 @@ def operator_terms(eng, refined, laplacian_type, eps: float = EPS):
     return None, r, None, 1.0, nat.EIG_LARGEST
   if not isinstance(laplacian_type, LaplacianType):
     raise TypeError("laplacian_type must be a LaplacianType")
-  _, rowsum = eng.row_stats(refined.s, refined.n, want_max=False, want_sum=True)
+  rowsum = getattr(refined, "rowsum", None)
+  if rowsum is None:
+    _, rowsum = eng.row_stats(refined.s, refined.n, want_max=False, want_sum=True)
   return terms_from_row_sums(rowsum, r, laplacian_type, eps)
 
 

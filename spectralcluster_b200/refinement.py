@@ -130,7 +130,7 @@ class Diffuse(AffinityRefinementOperation):
   """A A^T (reference :229-234) on the tcgen05 GEMM."""
 
   def refine(self, affinity):
-    return self._on_device(affinity, lambda eng, a, n: eng.diffuse(n, y=a))
+    return self._on_device(affinity, lambda eng, a, n: eng.diffuse(n, y=a)[0])
 
 
 class RowWiseNormalize(AffinityRefinementOperation):

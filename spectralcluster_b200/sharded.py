@@ -338,7 +338,7 @@ class DeviceBackend:
     hi, lo = y_full
     ld = hi.stride(0)
     c = self.dev.ctypes.c_void_p
-    eng.call("sc_gemm_nt_planes", eng.gemm_precision,
+    eng.call("sc_gemm_nt_planes", eng.diffuse_precision,
              c(hi.data_ptr() + 2 * a_row * ld), c(lo.data_ptr() + 2 * a_row * ld), ld, a_rows,
              c(hi.data_ptr() + 2 * b_row * ld), c(lo.data_ptr() + 2 * b_row * ld), ld, b_rows, n,
              c(s_block.data_ptr() + 4 * (s_row * s_block.stride(0) + b_row)), s_block.stride(0),

@@ -91,7 +91,8 @@ class SpectralClusterer:
     n = affinity.n
     refined = dev.run_refinement(eng, affinity.matrix, n, self.refinement_options,
                                  crop_vector=affinity.crop_vector,
-                                 a_symmetric=affinity.symmetric)
+                                 a_symmetric=affinity.symmetric,
+                                 diffuse_precision=eng.diffuse_precision)
     if not refined.symmetric:
       raise NotImplementedError(
           "this refinement sequence leaves a matrix that is not symmetric or diagonally similar "

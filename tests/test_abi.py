@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     assert name in nat.PROTOTYPES, "ctypes table lacks " + name
     assert len(nat.PROTOTYPES[name]) == argc, "arity mismatch for " + name
   assert set(nat.PROTOTYPES) == set(decl)
-  assert lib.sc_abi_version() == 1
+  assert lib.sc_abi_version() == nat.ABI_VERSION == 2
 
 
 def test_no_cuda_device_is_an_error_not_a_fallback():

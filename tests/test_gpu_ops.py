@@ -139,9 +139,9 @@ def test_diffuse_engines_agree(engine):
   old = engine.simt_below
   try:
     engine.simt_below = 10 ** 9
-    s_simt = engine.download_matrix(engine.diffuse(n, y=yd), n)
+    s_simt = engine.download_matrix(engine.diffuse(n, y=yd)[0], n)
     engine.simt_below = 0
-    s_tc = engine.download_matrix(engine.diffuse(n, y=yd), n)
+    s_tc = engine.download_matrix(engine.diffuse(n, y=yd)[0], n)
   finally:
     engine.simt_below = old
   want = y.astype(np.float64) @ y.astype(np.float64).T

@@ -75,7 +75,11 @@ class FakeEngine:
     self._rec("blur_thrsym", sigma, diag, sym, want_f32, want_planes)
     return ("y" if want_f32 else None, "hi" if want_planes else None, "lo" if want_planes else None)
 
-  def diffuse(self, n, y=None, hi=None, lo=None): return self._rec("diffuse", y, hi)
+  def diffuse(self, n, y=None, hi=None, lo=None, want_stats=False, precision=None):
+    self._rec("diffuse", y, hi, want_stats)
+    if want_stats:    # (rowmax fp32, rowsum fp64) from the GEMM epilogue
+      return "S", torch.ones(self.n, dtype=torch.float32) * 2.0, torch.ones(self.n, dtype=torch.float64) * 3.0
+    return "S", None, None
   def row_normalize(self, a, n): return self._rec("row_normalize")
 
   def row_stats(self, a, n, want_max=True, want_sum=True):
@@ -91,11 +95,13 @@ def test_planner_fuses_the_icassp_sequence():
   eng = FakeEngine(1000)
   opt = scb.RefinementOptions(refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
   out = dev.run_refinement(eng, "A", 1000, opt, crop_vector="cropvec")
-  assert names(eng) == ["blur_rowmax", "blur_thrsym", "diffuse", "row_stats"]
+  # RowWiseNormalize's row maxima (and the degree) come out of the Diffuse epilogue: no row_stats
+  assert names(eng) == ["blur_rowmax", "blur_thrsym", "diffuse"]
   assert eng.calls[0][1:] == (1.0, "cropvec")            # crop vector from the affinity epilogue
   assert eng.calls[1][3:] == (nat.SYMMETRIZE_MAX, False, True)   # planes only: Diffuse follows
-  assert eng.calls[2][1:] == (None, "hi")                # tensor-core Diffuse on the planes
+  assert eng.calls[2][1:] == (None, "hi", True)          # tensor-core Diffuse on the planes
   assert out.symmetric and torch.allclose(out.row_scale, torch.full((1000,), 0.5, dtype=torch.float64))
+  assert torch.allclose(out.rowsum, torch.full((1000,), 3.0, dtype=torch.float64))
 
 
 def test_planner_variants():
@@ -112,7 +118,8 @@ def test_planner_variants():
   eng = FakeEngine(20, tensor_cores=False)
   opt = scb.RefinementOptions(refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
   dev.run_refinement(eng, "A", 20, opt, crop_vector="c")
-  assert eng.calls[1][4:] == (True, False) and eng.calls[2][1:] == ("y", None)
+  assert eng.calls[1][4:] == (True, False) and eng.calls[2][1:] == ("y", None, False)
+  assert names(eng)[-1] == "row_stats"                   # SIMT GEMM: separate reduction pass
   # Percentile thresholding and threshold-without-symmetrize are not fusable
   eng = FakeEngine(300)
   opt = scb.RefinementOptions(thresholding_type=scb.ThresholdType.Percentile,

@@ -9,11 +9,11 @@ a = ap.parse_args()
 eng = dev.Engine.get(0); n = a.n
 y = eng.matrix(n); y.uniform_(0.0, 1.0)
 hi, lo = eng.split_planes(y, n); del y
-for _ in range(1): s = eng.diffuse(n, hi=hi, lo=lo); del s
+for _ in range(1): s = eng.diffuse(n, hi=hi, lo=lo)[0]; del s
 torch.cuda.synchronize()
 st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 st.record()
-for _ in range(a.iters): s = eng.diffuse(n, hi=hi, lo=lo); del s
+for _ in range(a.iters): s = eng.diffuse(n, hi=hi, lo=lo)[0]; del s
 en.record(); torch.cuda.synchronize()
 ms = st.elapsed_time(en) / a.iters
 print("N=%d pacing=%s diffuse %.1f ms  %.0f TFLOP/s algorithmic (2N^3)" % (
