@@ -15,8 +15,12 @@ on): N=65,536, d=256, ICASSP-2018 refinement sequence, GraphCut Laplacian, eigen
   cpu_baseline / --impl reference : the NumPy/SciPy/scikit-learn oracle (a restatement of the
           pure-Python reference, which cannot travel to the GPU box) on a bounded sample
 
-With --gpus N > 1 (torchrun) every rank clusters its own independent batch (weak scaling,
-replicas; the path has no data-path collective at this N -- see DESIGN.md "Multi-GPU").
+With --gpus N > 1 (torchrun) the default is STRONG scaling of ONE N=65,536 problem: every
+N x N matrix is row-sharded over the ranks (spectralcluster_b200/sharded.py, north_star's
+split), value = N / time of one predict_sharded(); the labels are checked against the generator's
+ground truth inside the run (exit code 3 on a mismatch).  `--workload replicas` runs one
+independent batch per GPU instead (weak scaling), `--workload sharded-refine` is BASELINE
+configs[3] (N=131,072 through Diffuse + row statistics).
 """
 
 import argparse
@@ -44,10 +48,14 @@ def parse():
   ap.add_argument("--speakers", type=int, default=6)
   ap.add_argument("--cpu-sample-n", type=int, default=2048)
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--workload", default="predict", choices=["predict", "sharded-refine", "sharded-predict"],
-                  help="predict: BASELINE configs[2] (default, replicas over GPUs); "
-                       "sharded-refine: configs[3], ONE problem row-sharded over the GPUs, timed "
-                       "region = affinity -> ... -> Diffuse -> row statistics (no eigensolve)")
+  ap.add_argument("--workload", default="auto",
+                  choices=["auto", "predict", "replicas", "sharded-refine", "sharded-predict"],
+                  help="auto: predict on 1 GPU, sharded-predict (ONE problem, strong scaling) on "
+                       "more; replicas: one independent batch per GPU; sharded-refine: configs[3], "
+                       "timed region = affinity -> ... -> Diffuse -> row statistics (no eigensolve)")
+  ap.add_argument("--cpu-stagewise-n", type=int, default=0,
+                  help="--impl reference: also time the CPU path stage by stage at this N "
+                       "(BASELINE.md section 3 planned 16384; 0 = skip)")
   return ap.parse_args()
 
 
@@ -182,7 +190,35 @@ def run_reference(args, rank):
               "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
+  if args.cpu_stagewise_n > 0:
+    line["cpu_stagewise"] = cpu_stagewise(args.cpu_stagewise_n, args.d, args.speakers)
   emit(line)
+
+
+def cpu_stagewise(n, d, speakers):
+  """Seconds per stage of the CPU path (oracle = NumPy/SciPy restatement of the reference) at a
+  size where the N x N stages still fit the host (N=16,384; the O(N^3)
+  np.linalg.eig is excluded -- SURVEY.md section 6 measured 138 s at N=8,192, exponent 2.96)."""
+  from oracle import spectral_oracle as orc
+  x = orc.synthetic_dvectors(n, d, speakers, seed=0)
+  out = {}
+  with all_host_threads():
+    def timed(name, fn):
+      t0 = time.perf_counter()
+      r = fn()
+      out[name] = time.perf_counter() - t0
+      return r
+    a = timed("affinity", lambda: orc.affinity(x))
+    a = timed("crop_diagonal", lambda: orc.crop_diagonal(a))
+    a = timed("gaussian_blur", lambda: orc.gaussian_blur(a, 1.0))
+    a = timed("row_threshold", lambda: orc.row_threshold(a, 0.95, 0.01))
+    a = timed("symmetrize", lambda: orc.symmetrize(a))
+    a = timed("diffuse", lambda: orc.diffuse(a))
+    a = timed("row_normalize", lambda: orc.row_normalize(a))
+    threads = host_threads()
+  return {"n": n, "seconds": out, "cores": int(threads),
+          "note": "eig (utils.py:59) and the Laplacian's two dense N^3 dots (laplacian.py:53,57) "
+                  "are not run at this size"}
 
 
 def run_sharded(args, eng, rank, world, dist):
@@ -249,57 +285,135 @@ def run_sharded(args, eng, rank, world, dist):
     dist.destroy_process_group()
 
 
+def dtype_string(eng):
+  from spectralcluster_b200 import _native as nat
+  scheme = {nat.GEMM_SPLIT3: "fp16x3 split (hi*hi + hi*lo + lo*hi)",
+            nat.GEMM_SPLIT2: "fp16x2 split ((hi+lo)*hi)",
+            nat.GEMM_SINGLE: "fp16 single (hi*hi)"}[eng.diffuse_precision]
+  return ("f32 storage; affinity: fp16x3 split tcgen05 MMAs; Diffuse: %s tcgen05 MMAs, f32 "
+          "two-level accumulate; f64 eigensolve and k-means" % scheme)
+
+
+def mma_per_product(eng):
+  from spectralcluster_b200 import _native as nat
+  return {nat.GEMM_SPLIT3: 3, nat.GEMM_SPLIT2: 2, nat.GEMM_SINGLE: 1}[eng.diffuse_precision]
+
+
+def load_peaks():
+  try:
+    return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    return {}
+
+
 def run_sharded_predict(args, eng, rank, world, dist):
-  """One N x N problem end to end (predict) with every matrix row-sharded over the ranks."""
+  """ONE N x N problem end to end (predict) with every matrix row-sharded over the ranks: the
+  north_star split, strong scaling.  value = N / device time of predict_sharded() with the
+  embeddings resident in HBM (CUDA events, max over ranks); e2e = the same call fed a host
+  ndarray (H2D of the embeddings and D2H of the labels inside the timed region)."""
   import torch
   from spectralcluster_b200 import _native as nat
-  from spectralcluster_b200 import sharded, synthetic
+  from spectralcluster_b200 import sharded, synthetic, utils
   n, d = args.n, args.d
   x, truth = synthetic.speaker_turn_dvectors(n, d, args.speakers, seed=0, return_labels=True)
   x = x.astype(np.float32)
+  x_pinned = torch.from_numpy(x).pin_memory()
+  x_dev = torch.from_numpy(x).to(eng.device)
   clusterer = make_clusterer()
+  group = dist if world > 1 else None
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
+  def check(labels, what):
+    if not np.array_equal(utils.enforce_ordered_labels(labels), utils.enforce_ordered_labels(truth)):
+      sys.stderr.write("bench: %s labels differ from the generator's ground truth\n" % what)
+      sys.stderr.flush()
+      os._exit(3)
+
+  # ---------------- e2e: host ndarray in, host labels out
   labels = None
   for _ in range(args.warmup):
-    labels = sharded.predict_sharded(clusterer, x, dist=dist if world > 1 else None)
+    labels = sharded.predict_sharded(clusterer, x_pinned.numpy(), dist=group)
   barrier()
-  launches0 = nat.load().sc_launch_count()
-  eng.start_profile()
   t0 = time.perf_counter()
   for _ in range(args.steps):
-    labels = sharded.predict_sharded(clusterer, x, dist=dist if world > 1 else None)
+    labels = sharded.predict_sharded(clusterer, x_pinned.numpy(), dist=group)
   barrier()
-  sec = time.perf_counter() - t0
+  e2e_s = time.perf_counter() - t0
+  check(labels, "e2e")
+
+  # ---------------- device-resident: embeddings already in HBM, CUDA events
+  for _ in range(max(1, args.warmup - 2)):
+    sharded.predict_sharded(clusterer, x_dev, dist=group)
+  barrier()
+  sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+  sampler.start()
+  launches0 = nat.load().sc_launch_count()
+  eng.start_profile()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  start.record()
+  for _ in range(args.steps):
+    labels = sharded.predict_sharded(clusterer, x_dev, dist=group)
+  stop.record()
+  barrier()
+  dev_ms = start.elapsed_time(stop)
   stages = eng.stop_profile()
   launches = nat.load().sc_launch_count() - launches0
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+  check(labels, "device-resident")
+  # one more step with the timeline markers on (outside the timed region)
+  refiner_trace = {}
+  if True:
+    from spectralcluster_b200 import device as dev
+    be = eng._sharded_backend
+    r = sharded.ShardedRefiner(be, clusterer.refinement_options, dist=group)
+    r.trace = []
+    r.run(x_dev, world, rank)
+    torch.cuda.synchronize()
+    refiner_trace = {r.trace[i][0]: r.trace[0][1].elapsed_time(r.trace[i][1])
+                     for i in range(1, len(r.trace))}
   if world > 1:
-    tt = torch.tensor([sec], dtype=torch.float64, device=eng.device)
+    tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=eng.device)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    sec = float(tt[0])
+    dev_ms, e2e_s = float(tt[0]), float(tt[1])
   if rank == 0:
-    from spectralcluster_b200 import utils
-    correct = bool(np.array_equal(utils.enforce_ordered_labels(labels),
-                                  utils.enforce_ordered_labels(truth)))
-    per = sec / args.steps
-    emit(({
-        "metric": "embeddings/sec through predict() (row-sharded)", "value": n / per,
+    per = dev_ms / args.steps
+    peaks = load_peaks()
+    tensor_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    gemm_ms = stages.get("sc_gemm_nt_planes", 0.0) / args.steps
+    # per rank: G/2 of the G^2 block products of the full 2 N^3 flop product (symmetry across ranks)
+    flops_rank = 2.0 * n * n * n / (2.0 * world) if world > 1 else 2.0 * n * n * n / 2.0
+    achieved = flops_rank / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
+    emit({
+        "metric": "embeddings/sec through predict()", "value": n / (per / 1e3),
         "unit": "embeddings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 storage; fp16x3 split tensor-core products; f64 eigensolve",
-        "data": "synthetic",
-        "config": {"workload": workload_name(n, d) + "; ONE problem row-sharded over %d GPU(s)" % world,
-                   "labels_match_generator_truth": correct,
-                   "details": {k: (v.tolist() if hasattr(v, "tolist") else v)
-                               for k, v in clusterer.last_details.items()}},
-        "e2e": {"value": n / per, "unit": "embeddings/s", "h2d_bytes_per_step": int(x.nbytes),
-                "d2h_bytes_per_step": int(labels.nbytes)},
+        "ms_per_step": per, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": dtype_string(eng), "data": "synthetic",
+        "config": {"workload": workload_name(n, d),
+                   "l2": "inputs larger than L2 (N x N fp32 = %.1f GB over %d GPUs)" % (n * n * 4 / 1e9, world),
+                   "parallelism": "ONE problem, N x N matrices row-sharded x%d (strong scaling)" % world,
+                   "transport": clusterer.last_details.get("transport"),
+                   "labels_match_generator_truth": True,
+                   "clusters_found": clusterer.last_details.get("n_clusters"),
+                   "eigensolver": clusterer.last_details.get("solver"),
+                   "lanczos_stats[matvecs,restarts,converged,m]": clusterer.last_details.get("lanczos_stats")},
+        "e2e": {"value": n * args.steps / e2e_s, "unit": "embeddings/s",
+                "h2d_bytes_per_step": int(x.nbytes) * world, "d2h_bytes_per_step": int(labels.nbytes) * world},
         "gpu_launches": int(launches),
-        "stage_ms_rank0": {k: v / args.steps for k, v in sorted(stages.items())}}))
+        "eigensolve_ms": stages.get("sc_eigh_extremal_sharded", 0.0) / args.steps,
+        "stage_ms_rank0": {k: v / args.steps for k, v in sorted(stages.items())},
+        "timeline_ms_rank0": refiner_trace,
+        "roofline": {"kernel": "k_gemm_tcgen05 (rank 0's Diffuse block products)", "bound": "tensor",
+                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                     "note": "achieved = this rank's share of the N^3 triangle-basis flop / CUDA-event "
+                             "time of its sc_gemm_nt_planes calls; %d MMAs issued per product"
+                             % mma_per_product(eng)},
+        "clocks": sampler.summary()})
   if world > 1:
     dist.destroy_process_group()
 
@@ -352,15 +466,20 @@ def main():
 
   torch.cuda.set_device(local_rank)
   if world > 1:
-    # keep stdout to the single JSON line (NCCL prints its version banner there at INFO/VERSION)
-    os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL's own log stays on (the StdoutGuard keeps fd 1 clean for the JSON line): the driver
+    # reads the communicator size from it
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   eng = dev.Engine.get(local_rank)
   n, d = args.n, args.d
-  if args.workload == "sharded-refine":
+  workload = args.workload
+  if workload == "auto":
+    workload = "predict" if world == 1 else "sharded-predict"
+  if workload == "sharded-refine":
     run_sharded(args, eng, rank, world, dist)
     return
-  if args.workload == "sharded-predict":
+  if workload == "sharded-predict":
     run_sharded_predict(args, eng, rank, world, dist)
     return
   # every rank clusters its own batch (different seed): weak scaling over independent units
@@ -451,8 +570,8 @@ def main():
   line = {
       "metric": "embeddings/sec through predict()", "value": value, "unit": "embeddings/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-      "dtype": "f32 storage; fp16x3 split tensor-core products with f32 accumulate; f64 eigensolve and k-means",
+      "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+      "dtype": dtype_string(eng),
       "data": "synthetic",
       "config": {"workload": workload_name(n, d), "l2": "inputs larger than L2 (N x N fp32 = %.1f GB)"
                  % (n * n * 4 / 1e9), "parallelism": "replicas x%d" % world,
@@ -468,14 +587,23 @@ def main():
                    "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                    "frac": (achieved / tensor_peak) if achieved else None, "traffic": traffic,
                    "peak_source": peak_note,
-                   "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse; the "
-                           "kernel issues 3x that in fp16 MMAs (hi*hi + hi*lo + lo*hi)"},
-      "roofline_hbm_stages": {
-          "blur_stats_pass_GBps": (n * n * 4 / 1e9) / (stages.get("sc_gaussian_blur_rowmax", 0) / args.steps / 1e3)
-          if stages.get("sc_gaussian_blur_rowmax") else None,
-          "blur_thrsym_pass_GBps": (n * n * 8 / 1e9) / (stages.get("sc_blur_threshold_symmetrize", 0) / args.steps / 1e3)
-          if stages.get("sc_blur_threshold_symmetrize") else None,
-          "peak_GBps": hbm_peak},
+                   "basis": "2 N^3 (full product, SURVEY.md 8(d))",
+                   "triangle_basis": {"achieved": achieved / 2 if achieved else None,
+                                      "frac": achieved / 2 / tensor_peak if achieved else None,
+                                      "note": "N^3: the kernel computes only the tiles that touch the "
+                                              "upper triangle and mirrors them"},
+                   "issued_mma": {"achieved": achieved / 2 * mma_per_product(eng) if achieved else None,
+                                  "frac": achieved / 2 * mma_per_product(eng) / tensor_peak if achieved else None,
+                                  "note": "fp16 MMA flop actually issued = %d x N^3" % mma_per_product(eng)},
+                   "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse"},
+      "roofline_hbm_stages": (lambda t1, t2: {
+          "blur_stats_pass_GBps": (n * n * 4 / 1e9) / (t1 / 1e3) if t1 else None,
+          "blur_thrsym_pass_GBps": (n * n * 8 / 1e9) / (t2 / 1e3) if t2 else None,
+          "fused_chain_GBps": (n * n * 12 / 1e9) / ((t1 + t2) / 1e3) if (t1 and t2) else None,
+          "fused_chain_frac": (n * n * 12 / 1e9) / ((t1 + t2) / 1e3) / hbm_peak if (t1 and t2) else None,
+          "basis": "12 B per affinity element (SURVEY.md 8(d)): read A, read A, write Y planes",
+          "peak_GBps": hbm_peak})(stages.get("sc_gaussian_blur_rowmax", 0) / args.steps,
+                                  stages.get("sc_blur_threshold_symmetrize", 0) / args.steps),
       "clocks": sampler.summary(),
   }
   if not args.no_cpu_baseline:

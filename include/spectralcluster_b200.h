@@ -179,10 +179,25 @@ int sc_row_stats_block(sc_context* ctx, const float* a, int64_t rows, int64_t co
 int sc_transpose(sc_context* ctx, const float* src, int64_t rows, int64_t cols, int64_t lds,
                  float* dst, int64_t ldd, void* stream);
 /* c[m,n] = (a_hi+a_lo)[m,k] (b_hi+b_lo)[n,k]^T : one (row block) x (peer row block) piece of
- * Diffuse (refinement.py:232-234) in the sharded pipeline. */
+ * Diffuse (refinement.py:232-234) in the sharded pipeline.  c_mirror (may be NULL) additionally
+ * receives the transpose, c_mirror[j*ldm + i] = c[i,j], from the same epilogue: it may point into
+ * a PEER GPU's row block of S (sc_ipc_open), which is how the symmetric half of the sharded
+ * product reaches its owner over NVLink without a separate exchange step. */
 int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi, const void* a_lo,
                       int64_t lda, int64_t m, const void* b_hi, const void* b_lo, int64_t ldb,
-                      int64_t n, int64_t k, float* c, int64_t ldc, void* stream);
+                      int64_t n, int64_t k, float* c, int64_t ldc, float* c_mirror, int64_t ldm,
+                      void* stream);
+
+/* ---- peer memory (one process per GPU, NVLink/NVSwitch) ------------------------------------ */
+/* CUDA IPC: export the allocation that contains dev_ptr (64-byte handle + byte offset of dev_ptr
+ * inside it); open it in another process of the same box (peer access is enabled lazily); close
+ * every mapping this process opened.  No reference counterpart. */
+int sc_ipc_export(sc_context* ctx, const void* dev_ptr, void* handle_out, int64_t* offset_out);
+int sc_ipc_open(sc_context* ctx, const void* handle, int64_t offset, void** out);
+int sc_ipc_close_all(sc_context* ctx);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on `stream`: with a peer-mapped source the copy engines pull
+ * the bytes over NVLink and no SM is involved. */
+int sc_memcpy_async(sc_context* ctx, void* dst, const void* src, int64_t bytes, void* stream);
 
 /* ---- utils.compute_sorted_eigenvectors (utils.py:44-71) ------------------------------ */
 /* The matrix decomposed is M = diag(delta) + sign * diag(left) S diag(right) with S symmetric

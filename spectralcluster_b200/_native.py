@@ -59,7 +59,11 @@ PROTOTYPES = {
     "sc_row_stats_block": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "sc_transpose": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_gemm_nt_planes": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64,
-                          c_i64, c_ptr, c_i64, c_ptr],
+                          c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr],
+    "sc_ipc_export": [c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_i64)],
+    "sc_ipc_open": [c_ptr, c_ptr, c_i64, ctypes.POINTER(c_ptr)],
+    "sc_ipc_close_all": [c_ptr],
+    "sc_memcpy_async": [c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_eigh_dense": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                       c_i64, c_ptr, c_ptr, c_ptr],
     "sc_eigh_extremal": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,

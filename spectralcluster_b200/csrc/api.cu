@@ -29,7 +29,7 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                     float* rowmax_offdiag, bool symmetric, int diag_shift, float* stat_rowmax,
-                    double* stat_rowsum, cudaStream_t st);
+                    double* stat_rowsum, float* mirror, int64_t ldm, cudaStream_t st);
 
 }  // namespace sc
 
@@ -107,7 +107,7 @@ extern "C" int sc_affinity_cosine(sc_context* ctx, int engine, int precision, co
   return gemm_nt_tcgen05(ctx, 1, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, d, a, lda,
                          rowmax_offdiag, /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr,
-                         as_stream(stream));
+                         nullptr, 0, as_stream(stream));
 }
 
 extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y,
@@ -129,7 +129,8 @@ extern "C" int sc_diffuse(sc_context* ctx, int engine, int precision, const floa
   }
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)hi, (const __half*)lo, ldh,
                          (const __half*)hi, (const __half*)lo, ldh, n, n, n, s, lds, nullptr,
-                         /*symmetric=*/true, /*diag_shift=*/0, rowmax, rowsum, as_stream(stream));
+                         /*symmetric=*/true, /*diag_shift=*/0, rowmax, rowsum, nullptr, 0,
+                         as_stream(stream));
 }
 
 // ---- row-block / general variants used by the row-sharded multi-GPU pipeline ----------------
@@ -145,17 +146,19 @@ extern "C" int sc_affinity_cosine_block(sc_context* ctx, int precision, const vo
   return gemm_nt_tcgen05(ctx, 1, precision, h + row_begin * ldh, l ? l + row_begin * ldh : nullptr,
                          ldh, h, l, ldh, row_count, n, d, a_block, lda, rowmax_offdiag_block,
                          /*symmetric=*/false, /*diag_shift=*/(int)row_begin, nullptr, nullptr,
-                         as_stream(stream));
+                         nullptr, 0, as_stream(stream));
 }
 
 extern "C" int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi,
                                  const void* a_lo, int64_t lda, int64_t m, const void* b_hi,
                                  const void* b_lo, int64_t ldb, int64_t n, int64_t k, float* c,
-                                 int64_t ldc, void* stream) {
+                                 int64_t ldc, float* c_mirror, int64_t ldm, void* stream) {
   SC_REQUIRE(ctx && a_hi && b_hi && c && m > 0 && n > 0 && k > 0, "sc_gemm_nt_planes: bad arguments");
   SC_REQUIRE((a_lo && b_lo) || precision == SC_GEMM_SINGLE || (a_lo && precision == SC_GEMM_SPLIT2),
              "sc_gemm_nt_planes: lo planes missing");
+  SC_REQUIRE(c_mirror == nullptr || ldm >= m, "sc_gemm_nt_planes: bad mirror leading dimension");
   return gemm_nt_tcgen05(ctx, 0, precision, (const __half*)a_hi, (const __half*)a_lo, lda,
                          (const __half*)b_hi, (const __half*)b_lo, ldb, m, n, k, c, ldc, nullptr,
-                         /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr, as_stream(stream));
+                         /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr, c_mirror, ldm,
+                         as_stream(stream));
 }

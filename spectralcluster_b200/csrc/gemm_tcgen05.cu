@@ -220,7 +220,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ TileTable tab, int M, int N, int K,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
                int diag_shift, unsigned int* __restrict__ pace, int pace_kb,
-               float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum) {
+               float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum,
+               float* __restrict__ mirror, int64_t ldm) {
   constexpr bool SPLIT = PREC >= 2;
   constexpr int STAGES = StageGeom<PREC>::STAGES;
   constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
@@ -465,6 +466,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
           }
         }
       }
+      if (!SYM && mirror != nullptr && row < M) {
+        // Row-sharded Diffuse: S(g,p) = Y_g Y_p^T is also S(p,g)^T.  `mirror` is rank p's row
+        // block of S mapped into this process (CUDA IPC over NVLink): the transposed tile is
+        // stored there straight from the accumulator registers -- the exchange step of the
+        // sharded product rides on the GEMM epilogue, tile by tile, instead of a separate
+        // transpose + send/recv after the last product.  Lanes hold consecutive rows, so every
+        // store instruction writes 128 contiguous bytes of one peer row.
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (col0 + i < N) mirror[(col0 + i) * ldm + row] = sum[i];
+      }
       if (SYM) {
         // mirror into the tiles that were skipped: target (col, row) lies in tile
         // (col/128, row/256), which is skipped iff col/128 >= 2 (row/256) + 2.  col0 is a
@@ -566,7 +578,7 @@ template <int PREC, int EPI, bool SYM>
 static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
                   const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
                   int64_t ldc, float* rowmax, int diag_shift, float* stat_rowmax,
-                  double* stat_rowsum, cudaStream_t st) {
+                  double* stat_rowsum, float* mirror, int64_t ldm, cudaStream_t st) {
   constexpr int STAGES = StageGeom<PREC>::STAGES;
   constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align*/ +
@@ -597,7 +609,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     SC_CUDA(cudaMemsetAsync(pace, 0, sizeof(unsigned int), st));
   }
   kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
-                                           pace, pace_kb, stat_rowmax, stat_rowsum); sc::launched();
+                                           pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }
@@ -606,7 +618,7 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
                     const __half* a_lo, int64_t lda, const __half* b_hi, const __half* b_lo,
                     int64_t ldb, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                     float* rowmax_offdiag, bool symmetric, int diag_shift, float* stat_rowmax,
-                    double* stat_rowsum, cudaStream_t st) {
+                    double* stat_rowsum, float* mirror, int64_t ldm, cudaStream_t st) {
   SC_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31),
              "tcgen05 GEMM: bad shape");
   SC_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0,
@@ -632,9 +644,10 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
   const int m = (int)M, n = (int)N, k = (int)K;
   // C = Y Y^T is symmetric when both operands are the same matrix: compute the upper tiles only
   const bool sym = symmetric && a_hi == b_hi && a_lo == b_lo && M == N && lda == ldb;
+  SC_REQUIRE(!(sym && mirror), "tcgen05 GEMM: a mirrored copy only makes sense for an off-diagonal block");
 #define SC_TC_LAUNCH(PR, EP, SY)                                                              \
   return launch<PR, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, diag_shift, \
-                            stat_rowmax, stat_rowsum, st)
+                            stat_rowmax, stat_rowsum, mirror, ldm, st)
 #define SC_TC_PREC(PR)                                                                        \
   do {                                                                                        \
     if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(PR, TC_EPI_AFFINITY, true);           \

@@ -10,9 +10,13 @@ row block [row_begin, row_end) of every N x N matrix:
      (the fused threshold/symmetrize rule needs m_i and m_j, SURVEY.md A.3);
   4. blur + threshold + symmetrize pass -> owned rows of Y as split fp16 planes;
   5. Diffuse: S = Y Y^T is symmetric, so rank g computes only S(g,g) and the blocks S(g, g+o),
-     o = 1..G/2: it fetches those peers' Y row blocks point-to-point (posted up front, landing
-     while the tensor cores work on the own diagonal block, which needs no traffic), and the
-     other half of its row block arrives as transposed copies of what the peers computed;
+     o = 1..G/2.  On NVLink (transport "peer": CUDA IPC mappings of the peers' buffers) the Y row
+     blocks it multiplies against are pulled by the copy engines on a side stream while the
+     tensor cores work on the own diagonal block -- no SM is taken from the persistent GEMM --
+     and the other half of every rank's row block is written by the peers' GEMM epilogues
+     themselves: each off-diagonal product stores its transposed tiles straight into the
+     owner's S over NVLink (compute and exchange in one kernel).  Transport "nccl"/"gloo" (CPU
+     tests, boxes without IPC) moves the same blocks with batched send/recv instead;
   6. row maxima / sums of S_block (RowWiseNormalize, Laplacian degree) are row-local.
 
 The orchestration below is backend-agnostic: `DeviceBackend` runs the CUDA kernels through the C
@@ -165,6 +169,9 @@ class ShardedRefiner:
     # gloo cannot send/recv device tensors: the single-GPU test configuration (two ranks sharing
     # one GPU over gloo) stages them through host memory; NCCL moves them GPU to GPU.
     staged = d.get_backend(self.group) == "gloo"
+    if self.group is not None:      # P2POp wants GLOBAL ranks; the plan speaks group-local ranks
+      sends = [(t, d.get_global_rank(self.group, peer)) for t, peer in sends]
+      recvs = [(t, d.get_global_rank(self.group, peer)) for t, peer in recvs]
     ops, landing = [], []
     for t, peer in recvs:
       if staged and t.is_cuda:
@@ -208,6 +215,49 @@ class ShardedRefiner:
       return [plane[p * plan.block:(p + 1) * plan.block] for plane in y_full]
 
     jobs = plan.compute_jobs() if world > 1 else []
+    transport = be.transport(self.dist, self.group) if world > 1 else "local"
+    self.last_transport = transport
+    if transport == "peer":
+      s_block = self._diffuse_peer(plan, y_full, jobs, n, yblk)
+    else:
+      s_block = self._diffuse_sendrecv(plan, y_full, jobs, n, yblk, world, rank)
+    self._mark("mirrored blocks")
+    rowmax, rowsum = be.row_stats_block(s_block, plan.rows, n)
+    self._mark("row stats")
+    return dict(plan=plan, s_block=s_block, rowmax=rowmax, rowsum=rowsum, y_planes=y_full)
+
+  def _diffuse_peer(self, plan, y_full, jobs, n, yblk):
+    """NVLink peer-memory schedule (one process per GPU, buffers mapped with CUDA IPC)."""
+    be, rank = self.backend, plan.rank
+    s_block = be.new_block(plan.rows, n)
+    peers = be.peer_buffers(self.dist, self.group, y_full, s_block)
+    # Everybody's Y block is written and everybody is done with the affinity arena (S lives in
+    # it): a one-element all-reduce, stream-ordered, no host stall.
+    be.stream_barrier(self.dist, self.group)
+    self._mark("Y blocks visible")
+    n_planes = be.b_planes_needed()               # split2 / single read only the hi plane of B
+    pulls = []
+    for p, _, (c0, c1) in jobs:
+      lo = plan.rows_of(p)[0]
+      pulls.append(be.pull_rows([pl for pl in y_full[:n_planes]], peers[p]["y"][:n_planes],
+                                lo + c0, c1 - c0))
+    be.gemm_block(y_full, plan.row_begin, plan.rows, plan.row_begin, plan.rows, n, s_block, 0)
+    self._mark("own block")
+    ld = s_block.stride(0)
+    for (p, (r0, r1), (c0, c1)), ready in zip(jobs, pulls):
+      be.wait_pull(ready)
+      lo = plan.rows_of(p)[0]
+      # S(p, rank)[c0:c1, r0:r1] = S(rank, p)[r0:r1, c0:c1]^T, stored by this GEMM's epilogue
+      mirror = peers[p]["s"] + 4 * (c0 * ld + plan.row_begin + r0)
+      be.gemm_block(y_full, plan.row_begin + r0, r1 - r0, lo + c0, c1 - c0, n, s_block, r0,
+                    mirror=mirror, ldm=ld)
+    self._mark("computed blocks")
+    be.stream_barrier(self.dist, self.group)      # every peer's mirrored tiles have landed
+    return s_block
+
+  def _diffuse_sendrecv(self, plan, y_full, jobs, n, yblk, world, rank):
+    """send/recv schedule (NCCL without IPC, gloo in the CPU tests, and world == 1)."""
+    be = self.backend
     recv_works, all_works = [], []
     be.reserve_comm_sms(world > 1)     # leave SMs to the send/recv kernels during the GEMMs
     try:
@@ -239,10 +289,7 @@ class ShardedRefiner:
         w.wait()
       for (buf, q), (_, (r0, r1), (c0, c1)) in zip(incoming, plan.mirror_jobs()):
         be.place_block(s_block, c0, plan.rows_of(q)[0] + r0, buf)
-    self._mark("mirrored blocks")
-    rowmax, rowsum = be.row_stats_block(s_block, plan.rows, n)
-    self._mark("row stats")
-    return dict(plan=plan, s_block=s_block, rowmax=rowmax, rowsum=rowsum, y_planes=y_full)
+    return s_block
 
   def _all_gather_blocks(self, full, plan):
     """full[p*block:(p+1)*block] <- rank p's slice (equal, padded blocks)."""
@@ -262,6 +309,8 @@ class DeviceBackend:
     # add up to >100 GB per GPU and re-allocating them costs ~1 s of cudaMalloc/cudaFree per step.
     # (A result that must survive the next run() has to be cloned by the caller.)
     self._buffers = {}
+    self._peer_ok, self.peer_error = None, None
+    self._peer_maps, self._flag, self._copy_stream = {}, None, None
 
   def _buffer(self, tag, shape, dtype):
     key = (tag, tuple(shape), dtype)
@@ -332,8 +381,10 @@ class DeviceBackend:
              nat.SYMMETRIZE_MAX if sym_max else nat.SYMMETRIZE_AVERAGE, None, 0,
              c(hi.data_ptr() + off), c(lo.data_ptr() + off), hi.stride(0), eng.stream)
 
-  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block, s_row):
-    """s_block[s_row:s_row+a_rows, b_row:b_row+b_rows] = Y[a_row:+a_rows] Y[b_row:+b_rows]^T."""
+  def gemm_block(self, y_full, a_row, a_rows, b_row, b_rows, n, s_block, s_row, mirror=None,
+                 ldm=0):
+    """s_block[s_row:s_row+a_rows, b_row:b_row+b_rows] = Y[a_row:+a_rows] Y[b_row:+b_rows]^T;
+    `mirror` (a raw device address, possibly in a peer GPU) also receives the transpose."""
     eng = self.eng
     hi, lo = y_full
     ld = hi.stride(0)
@@ -342,7 +393,105 @@ class DeviceBackend:
              c(hi.data_ptr() + 2 * a_row * ld), c(lo.data_ptr() + 2 * a_row * ld), ld, a_rows,
              c(hi.data_ptr() + 2 * b_row * ld), c(lo.data_ptr() + 2 * b_row * ld), ld, b_rows, n,
              c(s_block.data_ptr() + 4 * (s_row * s_block.stride(0) + b_row)), s_block.stride(0),
-             eng.stream)
+             c(mirror) if mirror else None, int(ldm), eng.stream)
+
+  # ---- NVLink peer memory (CUDA IPC) -------------------------------------------------------
+  def transport(self, dist, group):
+    """"peer" (IPC-mapped buffers, copy-engine pulls + epilogue pushes) when every rank of the
+    group drives its own GPU of this box over NCCL; else "nccl" / "gloo" send/recv."""
+    import os
+    backend = dist.get_backend(group)
+    if backend != "nccl":
+      return backend
+    if os.environ.get("SCB_SHARDED_TRANSPORT", "peer") != "peer":
+      return "nccl"
+    if self._peer_ok is None:
+      self._peer_ok = self._probe_peer(dist, group)
+    return "peer" if self._peer_ok else "nccl"
+
+  def _probe_peer(self, dist, group):
+    """All ranks on distinct devices of one host, and an IPC round trip works."""
+    import socket
+    t = self.t
+    world = dist.get_world_size(group)
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), self.eng.device_index), group=group)
+    ok = len(set(h for h, _ in info)) == 1 and len(set(d for _, d in info)) == world
+    if ok:
+      try:
+        probe = self._buffer("ipc_probe", (1 << 18,), t.float32)
+        self._open_all(dist, group, [probe])
+      except Exception as e:                      # IPC unavailable (container policy, driver)
+        self.peer_error = str(e)
+        ok = False
+    flag = t.tensor([1 if ok else 0], device=self.eng.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag[0]))
+
+  def _open_all(self, dist, group, tensors):
+    """[{name index: raw address in this process} per rank] for the given local tensors."""
+    import ctypes
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = []
+    for tn in tensors:
+      handle = ctypes.create_string_buffer(64)
+      off = ctypes.c_int64(0)
+      self.nat.call("sc_ipc_export", self.eng.ctx, self._p(tn), handle, ctypes.byref(off))
+      mine.append((handle.raw, int(off.value)))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    out = []
+    for q in range(world):
+      if q == rank:
+        out.append([tn.data_ptr() for tn in tensors])
+        continue
+      addrs = []
+      for raw, off in everyone[q]:
+        ptr = ctypes.c_void_p()
+        self.nat.call("sc_ipc_open", self.eng.ctx, ctypes.create_string_buffer(raw, 64), off,
+                      ctypes.byref(ptr))
+        addrs.append(int(ptr.value))
+      out.append(addrs)
+    return out
+
+  def peer_buffers(self, dist, group, y_full, s_block):
+    """{rank: {"y": [hi address, lo address], "s": address}} of every rank's persistent Y planes
+    and S row block, mapped once per buffer set."""
+    key = (y_full[0].data_ptr(), y_full[1].data_ptr(), s_block.data_ptr())
+    cached = self._peer_maps.get(key)
+    if cached is None:
+      addrs = self._open_all(dist, group, [y_full[0], y_full[1], s_block])
+      cached = [dict(y=a[:2], s=a[2]) for a in addrs]
+      self._peer_maps = {key: cached}             # buffers changed shape: older maps are stale
+    return cached
+
+  def stream_barrier(self, dist, group):
+    if self._flag is None:
+      self._flag = self.t.zeros((1,), dtype=self.t.float32, device=self.eng.device)
+    dist.all_reduce(self._flag, group=group)
+
+  def b_planes_needed(self):
+    return 2 if self.eng.diffuse_precision == self.nat.GEMM_SPLIT3 else 1
+
+  def pull_rows(self, local_planes, peer_addrs, row, rows):
+    """Copy rows [row, row+rows) of the peer's planes into the same rows of the local planes on
+    the copy stream; returns the event the consumer waits for."""
+    t = self.t
+    if self._copy_stream is None:
+      self._copy_stream = t.cuda.Stream(device=self.eng.device)
+    side = self._copy_stream
+    side.wait_stream(t.cuda.current_stream(self.eng.device))
+    c = self.dev.ctypes.c_void_p
+    for plane, addr in zip(local_planes, peer_addrs):
+      off = row * plane.stride(0) * plane.element_size()
+      self.nat.call("sc_memcpy_async", self.eng.ctx, c(plane.data_ptr() + off), c(addr + off),
+                    rows * plane.stride(0) * plane.element_size(), c(side.cuda_stream))
+    ev = t.cuda.Event()
+    ev.record(side)
+    return ev
+
+  def wait_pull(self, ev):
+    self.t.cuda.current_stream(self.eng.device).wait_event(ev)
 
   comm_sms = 16
 
@@ -381,10 +530,38 @@ class DeviceBackend:
     return mx, sm
 
 
-def predict_sharded(clusterer, embeddings: np.ndarray, dist=None, group=None) -> np.ndarray:
+def check_sharded_options(clusterer, num_embeddings: int):
+  """The argument / option checks of predict() that also apply to predict_sharded(): a clusterer
+  configured with something this path does not implement must fail here, not silently return
+  labels that differ from predict() and from the reference."""
+  from . import custom_distance_kmeans, utils
+  if clusterer.autotune or not clusterer.max_clusters:
+    raise NotImplementedError("predict_sharded: needs max_clusters and no AutoTune")
+  if clusterer.affinity_function is not utils.compute_affinity_matrix:
+    raise NotImplementedError("predict_sharded: only the built-in cosine affinity is sharded")
+  if num_embeddings < clusterer.fallback_options.spectral_min_embeddings:
+    raise NotImplementedError("predict_sharded: the fallback clusterer is not sharded")
+  if clusterer.max_spectral_size is not None and num_embeddings > clusterer.max_spectral_size:
+    raise NotImplementedError("predict_sharded: max_spectral_size pre-clustering is not sharded "
+                              "(sharding is the exact alternative to it)")
+  if clusterer.min_clusters == 1:
+    raise NotImplementedError("predict_sharded: single-cluster detection is not sharded")
+  if clusterer.constraint_options:
+    raise NotImplementedError("predict_sharded: constraints are not sharded")
+  limit = clusterer.max_clusters + 1
+  if limit > 32:
+    raise NotImplementedError("predict_sharded: max_clusters <= 31 (extremal eigensolver)")
+  basis = max(2 * limit + 32, 64)
+  if num_embeddings < 4 * basis:
+    raise ValueError("predict_sharded: n=%d is too small for the Lanczos basis (%d vectors); "
+                     "use predict()" % (num_embeddings, basis))
+
+
+def predict_sharded(clusterer, embeddings, dist=None, group=None) -> np.ndarray:
   """SpectralClusterer.predict() with every N x N matrix row-sharded over the ranks of `group`
   (BASELINE.json configs[3]: N = 131,072 does not fit one GPU).  Every rank passes the same
-  embeddings and receives the same labels.
+  embeddings (a host ndarray, or a float32/float64 tensor already on this rank's GPU) and
+  receives the same labels.
 
   Refinement as in ShardedRefiner; row maxima / sums all-gathered (2 N doubles); eigensolve by the
   sharded thick-restart Lanczos (each matvec streams the local row block and all-gathers N
@@ -394,23 +571,29 @@ def predict_sharded(clusterer, embeddings: np.ndarray, dist=None, group=None) ->
   from . import custom_distance_kmeans, device as dev, laplacian as lap, utils
   from . import refinement as rf
   t = dev.torch()
-  if not isinstance(embeddings, np.ndarray):
+  on_device = t.is_tensor(embeddings) and embeddings.is_cuda
+  if not on_device and not isinstance(embeddings, np.ndarray):
     raise TypeError("embeddings must be a numpy array")
   if len(embeddings.shape) != 2:
     raise ValueError("embeddings must be 2-dimensional")
-  if clusterer.autotune or not clusterer.max_clusters:
-    raise NotImplementedError("predict_sharded: needs max_clusters and no AutoTune")
+  check_sharded_options(clusterer, int(embeddings.shape[0]))
   world = dist.get_world_size(group) if dist is not None else 1
   rank = dist.get_rank(group) if dist is not None else 0
   eng = dev.Engine.get()
-  be = DeviceBackend(eng)
-  x = np.ascontiguousarray(embeddings)
-  if x.dtype not in (np.float32, np.float64):
-    x = x.astype(np.float64)
-  x_dev = t.from_numpy(x).to(eng.device, non_blocking=True)
-  n = x.shape[0]
+  be = getattr(eng, "_sharded_backend", None)
+  if be is None:                 # persistent: N x N-scale buffers and the peers' IPC mappings
+    be = eng._sharded_backend = DeviceBackend(eng)
+  if on_device:
+    x_dev = embeddings
+  else:
+    x = np.ascontiguousarray(embeddings)
+    if x.dtype not in (np.float32, np.float64):
+      x = x.astype(np.float64)
+    x_dev = t.from_numpy(x).to(eng.device, non_blocking=True)
+  n = int(x_dev.shape[0])
   opt = clusterer.refinement_options
-  res = ShardedRefiner(be, opt, dist=dist if world > 1 else None, group=group).run(x_dev, world, rank)
+  refiner = ShardedRefiner(be, opt, dist=dist if world > 1 else None, group=group)
+  res = refiner.run(x_dev, world, rank)
   plan = res["plan"]
   length = world * plan.block
 
@@ -462,6 +645,7 @@ def predict_sharded(clusterer, embeddings: np.ndarray, dist=None, group=None) ->
         descend=False)
   clusterer.last_details = dict(eigenvalues=w.copy(), n_clusters_raw=k, max_gap=gap,
                                 solver="lanczos-sharded x%d" % world,
+                                transport=getattr(refiner, "last_transport", "local"),
                                 lanczos_stats=stats.tolist())
   return clusterer._cluster_embeddings(eng, v, k)
 
