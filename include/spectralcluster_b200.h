@@ -143,6 +143,12 @@ int sc_diffuse(sc_context* ctx, int engine, int precision, const float* y, int64
 int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda, double* rowmax,
                  double* rowsum, void* stream);
 
+/* The reductions behind fallback_clusterer.check_single_cluster (fallback_clusterer.py:127-187):
+ * out_host[0] = min a, [1] = sum a, [2] = sum a^2 over all n^2 entries (np.std, :154),
+ * [3] = min_i a[i][i+1] (np.diag(affinity, k=1).min(), :148-150).  SYNCHRONOUS. */
+int sc_affinity_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda, double* out_host,
+                      void* stream);
+
 /* RowWiseNormalize.refine (refinement.py:240-245), materialised.  out may alias a. */
 int sc_row_normalize(sc_context* ctx, const float* a, int64_t n, int64_t lda, float* out,
                      int64_t ldo, void* stream);

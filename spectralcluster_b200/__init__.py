@@ -8,7 +8,7 @@ are intentionally absent -- see DESIGN.md section 1.
 """
 
 from . import (autotune, configs, custom_distance_kmeans, fallback_clusterer, laplacian,
-               refinement, spectral_clusterer, utils)
+               naive_clusterer, refinement, spectral_clusterer, utils)
 
 __version__ = "0.1.0"
 
@@ -28,5 +28,5 @@ for _module, _names in _EXPORTS.items():
 
 __all__ = sorted(n for names in _EXPORTS.values() for n in names) + [
     "autotune", "configs", "custom_distance_kmeans", "fallback_clusterer", "laplacian",
-    "refinement", "spectral_clusterer", "utils"]
+    "naive_clusterer", "refinement", "spectral_clusterer", "utils"]
 del _module, _names, _name

@@ -236,6 +236,63 @@ __global__ void k_row_stats(const float* __restrict__ a, int64_t n /*columns*/, 
   }
 }
 
+// ------------------------------------------------------------------ single-cluster statistics
+// fallback_clusterer.check_single_cluster (fallback_clusterer.py:127-187) needs three reductions
+// of the affinity: its minimum (AllAffinity, :143), the minimum of the first super-diagonal
+// (NeighborAffinity, :148-150) and np.std over all n^2 entries (AffinityStd, :154).  One
+// streaming pass, fp64 accumulation; per-row partials, then a single-block finish.
+__global__ void k_affinity_row_stats(const float* __restrict__ a, int64_t n, int64_t lda,
+                                     double* __restrict__ part /*[3][n]*/) {
+  __shared__ double red[32];
+  const int64_t i = blockIdx.x;
+  const float* r = a + i * lda;
+  double mn = INFINITY, s = 0.0, q2 = 0.0;
+  const int64_t n4 = n & ~(int64_t)3;
+  for (int64_t j = (int64_t)threadIdx.x * 4; j < n4; j += (int64_t)blockDim.x * 4) {
+    const float4 q = ld_stream4(r + j);
+    mn = fmin(mn, (double)fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
+    s += ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
+    q2 += ((double)q.x * q.x + (double)q.y * q.y) + ((double)q.z * q.z + (double)q.w * q.w);
+  }
+  for (int64_t j = n4 + threadIdx.x; j < n; j += blockDim.x) {
+    const double x = (double)r[j];
+    mn = fmin(mn, x);
+    s += x;
+    q2 += x * x;
+  }
+  mn = -block_maxd(-mn, red);
+  s = block_sum(s, red);
+  q2 = block_sum(q2, red);
+  if (threadIdx.x == 0) {
+    part[i] = mn;
+    part[n + i] = s;
+    part[2 * n + i] = q2;
+  }
+}
+
+// out[0] = min, out[1] = sum, out[2] = sum of squares, out[3] = min_i a[i][i+1] (+inf if n == 1)
+__global__ void k_affinity_stats_finish(const double* __restrict__ part, const float* __restrict__ a,
+                                        int64_t n, int64_t lda, double* __restrict__ out) {
+  __shared__ double red[32];
+  double mn = INFINITY, s = 0.0, q2 = 0.0, nb = INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    mn = fmin(mn, part[i]);
+    s += part[n + i];
+    q2 += part[2 * n + i];
+    if (i + 1 < n) nb = fmin(nb, (double)a[i * lda + i + 1]);
+  }
+  mn = -block_maxd(-mn, red);
+  s = block_sum(s, red);
+  q2 = block_sum(q2, red);
+  nb = -block_maxd(-nb, red);
+  if (threadIdx.x == 0) {
+    out[0] = mn;
+    out[1] = s;
+    out[2] = q2;
+    out[3] = nb;
+  }
+}
+
 // ------------------------------------------------------------------ row-wise normalise
 __global__ void k_row_normalize(const float* __restrict__ a, int64_t n, int64_t lda,
                                 float* __restrict__ out, int64_t ldo) {
@@ -346,6 +403,22 @@ extern "C" int sc_row_stats(sc_context* ctx, const float* a, int64_t n, int64_t 
   SC_REQUIRE(vec_ok_f32(a, lda), "sc_row_stats: `a` needs a 16-byte aligned base and lda %% 4 == 0");
   k_row_stats<<<(unsigned)n, 256, 0, as_stream(stream)>>>(a, n, lda, rowmax, rowsum); sc::launched();
   SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_affinity_stats(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                                 double* out_host, void* stream) {
+  SC_REQUIRE(ctx && a && out_host && n > 0, "sc_affinity_stats: bad arguments");
+  SC_REQUIRE(vec_ok_f32(a, lda), "sc_affinity_stats: `a` needs a 16-byte aligned base and lda %% 4 == 0");
+  cudaStream_t st = as_stream(stream);
+  Scratch part;
+  SC_CUDA(part.alloc(sizeof(double) * (size_t)(3 * n + 4), st));
+  double* p = part.as<double>();
+  k_affinity_row_stats<<<(unsigned)n, 256, 0, st>>>(a, n, lda, p); sc::launched();
+  k_affinity_stats_finish<<<1, 1024, 0, st>>>(p, a, n, lda, p + 3 * n); sc::launched();
+  SC_LAUNCH_CHECK();
+  SC_CUDA(cudaMemcpyAsync(out_host, p + 3 * n, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

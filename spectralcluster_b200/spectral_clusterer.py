@@ -4,9 +4,10 @@ _compute_eigenvectors_ncluster :108-168, predict :201-314) whose arithmetic runs
 
 predict(): one H2D copy of the [N, d] embeddings, every N x N intermediate stays in HBM
 (affinity GEMM -> fused refinement -> Diffuse GEMM -> row statistics -> symmetric eigensolve ->
-k-means), one D2H copy of N labels.  Branches of the reference that leave the hot path
-(fallback clusterer, max_spectral_size pre-clustering, constraints, single-cluster checks,
-non-symmetrisable eigenproblems) raise NotImplementedError instead of falling back to a CPU.
+k-means), one D2H copy of N labels.  The callers around the path follow the reference: the
+fallback clusterer for tiny inputs and the max_spectral_size AHC pre-clustering are host code
+(scikit-learn, as in the reference), the single-cluster checks are device reductions over the
+resident affinity.
 """
 
 from __future__ import annotations
@@ -153,6 +154,17 @@ class SpectralClusterer:
     _, v, k, gap = self._eigen_on_device(eng, da)
     return v.to("cpu").numpy(), k, gap
 
+  def _reduce_size_and_predict(self, embeddings: np.ndarray) -> np.ndarray:
+    """spectral_clusterer.py:170-199: complete-linkage cosine AHC down to `max_spectral_size`
+    clusters (scikit-learn, host -- the reference's own lossy answer to large N; the device path
+    does not need it, BASELINE configs[3] shards the exact problem instead), spectral clustering
+    of the cluster centroids on the device, labels chained back."""
+    from sklearn.cluster import AgglomerativeClustering
+    pre = AgglomerativeClustering(n_clusters=self.max_spectral_size, metric="cosine",
+                                  linkage="complete").fit_predict(embeddings)
+    centroids = utils.get_cluster_centroids(embeddings, pre)
+    return utils.chain_labels(pre, self.predict(centroids))
+
   # ------------------------------------------------------------------ predict
   def predict(self, embeddings: np.ndarray, constraint_matrix=None) -> np.ndarray:
     """Cluster the rows of `embeddings` ([n_samples, n_features] ndarray) -> int64 labels."""
@@ -162,7 +174,8 @@ class SpectralClusterer:
     if len(embeddings.shape) != 2:
       raise ValueError("embeddings must be 2-dimensional")
     if num_embeddings < self.fallback_options.spectral_min_embeddings:
-      raise NotImplementedError("the fallback clusterer is outside the B200 hot path")
+      # too few embeddings for a spectrum (spectral_clusterer.py:230-234): host fallback clusterer
+      return fallback_clusterer.FallbackClusterer(self.fallback_options).predict(embeddings)
     if self.max_spectral_size is not None and num_embeddings > self.max_spectral_size:
       if constraint_matrix is not None:
         raise RuntimeError("Cannot handle constraint_matrix when max_spectral_size is set")
@@ -170,11 +183,7 @@ class SpectralClusterer:
           (self.max_clusters and self.max_spectral_size <= self.max_clusters) or
           (self.min_clusters and self.max_spectral_size <= self.min_clusters)):
         raise ValueError("max_spectral_size should be a relatively big number")
-      raise NotImplementedError(
-          "max_spectral_size pre-clustering (AHC) is outside the B200 hot path; the B200 path "
-          "handles the full N exactly")
-    if self.min_clusters == 1:
-      raise NotImplementedError("single-cluster detection is outside the B200 hot path")
+      return self._reduce_size_and_predict(embeddings)
     if constraint_matrix is not None and self.constraint_options:
       raise NotImplementedError("constraints are outside the B200 hot path")
 
@@ -193,6 +202,11 @@ class SpectralClusterer:
       host = np.asarray(self.affinity_function(embeddings))
       affinity = DeviceAffinity(eng.upload_matrix(host), num_embeddings, None,
                                 bool(np.allclose(host, host.T, rtol=1e-6, atol=1e-9)))
+
+    if self.min_clusters == 1:
+      # single-vs-multi cluster decision on the resident affinity (spectral_clusterer.py:253-256)
+      if fallback_clusterer.check_single_cluster(self.fallback_options, embeddings, affinity):
+        return np.array([0] * num_embeddings)
 
     if self.autotune:
       if RefinementName.RowWiseThreshold not in sequence:

@@ -102,3 +102,25 @@ def enforce_ordered_labels(labels: np.ndarray) -> np.ndarray:
   out = labels.copy()
   out[...] = rank[inverse].reshape(labels.shape)
   return out
+
+
+def get_cluster_centroids(embeddings: np.ndarray, labels: np.ndarray) -> np.ndarray:
+  """Mean embedding of every cluster 0..max(labels) (utils.py:159-177), as one segmented sum."""
+  labels = np.asarray(labels).astype(np.int64)
+  k = int(labels.max()) + 1
+  sums = np.zeros((k, embeddings.shape[1]), dtype=np.result_type(embeddings.dtype, np.float64))
+  np.add.at(sums, labels, embeddings)
+  counts = np.bincount(labels, minlength=k).astype(sums.dtype)
+  return sums / counts[:, None]        # an empty cluster id gives NaN, like np.mean of no rows
+
+
+def chain_labels(pre_labels: typing.Optional[np.ndarray], main_labels: np.ndarray) -> np.ndarray:
+  """Compose pre-clusterer labels with the labels of its clusters (utils.py:180-206).  The result
+  is float64 like the reference's (np.zeros default dtype)."""
+  if pre_labels is None:
+    return main_labels
+  groups = int(max(pre_labels) + 1)
+  if groups != main_labels.shape[0]:
+    raise ValueError("pre_labels has {} values while main_labels has {} rows.".format(
+        groups, main_labels.shape[0]))
+  return np.asarray(main_labels)[np.asarray(pre_labels).astype(np.int64)].astype(np.float64)

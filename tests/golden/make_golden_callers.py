@@ -1,0 +1,108 @@
+"""Golden vectors for the callers either side of the hot path:
+naive / fallback clusterers, get_cluster_centroids / chain_labels, check_single_cluster,
+predict() with min_clusters=1, spectral_min_embeddings and max_spectral_size.
+
+Run in the build container only (imports the UNMODIFIED reference from /root/reference):
+
+    python tests/golden/make_golden_callers.py
+
+Outputs tests/golden/callers/*.npz -- every array in them was produced by the reference.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import spectralcluster as ref  # noqa: E402
+from spectralcluster import fallback_clusterer as fb, naive_clusterer as nc, utils  # noqa: E402
+from oracle import spectral_oracle as orc  # noqa: E402
+
+OUT = os.path.join(HERE, "callers")
+
+
+def blobs(n, d, k, seed, spread=0.1):
+  rng = np.random.default_rng(seed)
+  centres = np.eye(d)[:k] + 0.05 * rng.standard_normal((k, d))
+  lab = rng.integers(0, k, n)
+  return centres[lab] + spread * rng.standard_normal((n, d))
+
+
+def main():
+  os.makedirs(OUT, exist_ok=True)
+  # ---- naive clusterer (naive_clusterer.py:58-105)
+  x = blobs(240, 8, 4, seed=11)
+  cases = [(0.5, -1.0), (0.7, 0.9), (0.9, 0.97)]
+  np.savez(os.path.join(OUT, "naive.npz"), x=x, thresholds=np.array(cases),
+           labels=np.stack([nc.NaiveClusterer(t, None if a < 0 else a).predict(x)
+                            for t, a in cases]))
+  # ---- fallback clusterer, both types (fallback_clusterer.py:95-124)
+  x = blobs(120, 6, 3, seed=5)
+  np.savez(
+      os.path.join(OUT, "fallback.npz"), x=x,
+      naive=fb.FallbackClusterer(fb.FallbackOptions(
+          fallback_clusterer_type=fb.FallbackClustererType.Naive, naive_threshold=0.6)).predict(x),
+      agglomerative=fb.FallbackClusterer(fb.FallbackOptions(
+          fallback_clusterer_type=fb.FallbackClustererType.Agglomerative,
+          agglomerative_threshold=0.4)).predict(x))
+  # ---- utils.get_cluster_centroids / chain_labels (utils.py:159-206)
+  rng = np.random.default_rng(2)
+  x = rng.standard_normal((300, 7))
+  pre = rng.permutation(np.arange(300) % 13)
+  main_labels = rng.integers(0, 4, 13)
+  np.savez(os.path.join(OUT, "utils.npz"), x=x, pre=pre, main=main_labels,
+           centroids=utils.get_cluster_centroids(x, pre),
+           chained=utils.chain_labels(pre, main_labels))
+  # ---- check_single_cluster on affinities (fallback_clusterer.py:127-187)
+  one = orc.affinity(blobs(90, 16, 1, seed=3, spread=0.05))
+  many = orc.affinity(blobs(90, 16, 3, seed=4, spread=0.05))
+  conds = [("AllAffinity", 0.75), ("AllAffinity", 0.999), ("NeighborAffinity", 0.75),
+           ("NeighborAffinity", 0.999), ("AffinityStd", 0.05), ("AffinityStd", 0.001),
+           ("AffinityGmmBic", 0.0)]
+  verdicts = []
+  for a in (one, many):
+    for name, thr in conds:
+      opt = fb.FallbackOptions(single_cluster_condition=getattr(fb.SingleClusterCondition, name),
+                               single_cluster_affinity_threshold=thr)
+      verdicts.append(bool(fb.check_single_cluster(opt, None, a)))
+  np.savez(os.path.join(OUT, "single_cluster.npz"), one=one, many=many,
+           conditions=np.array([c for c, _ in conds]), thresholds=np.array([t for _, t in conds]),
+           verdicts=np.array(verdicts).reshape(2, len(conds)))
+  # ---- predict(): min_clusters=1 with each condition; tiny-input fallback; max_spectral_size
+  x1 = blobs(400, 32, 1, seed=7, spread=0.05)
+  x4 = orc.synthetic_dvectors(400, 32, 4, seed=7)
+  out = dict(x1=x1, x4=x4)
+  for tag, name, thr in (("all", "AllAffinity", 0.6), ("nbr", "NeighborAffinity", 0.6),
+                         ("std", "AffinityStd", 0.05), ("bic", "AffinityGmmBic", 0.0)):
+    for dn, data in (("x1", x1), ("x4", x4)):
+      c = ref.SpectralClusterer(
+          min_clusters=1, max_clusters=7, laplacian_type=ref.LaplacianType.GraphCut,
+          fallback_options=fb.FallbackOptions(
+              single_cluster_condition=getattr(fb.SingleClusterCondition, name),
+              single_cluster_affinity_threshold=thr),
+          refinement_options=ref.RefinementOptions(
+              gaussian_blur_sigma=1, p_percentile=0.95,
+              refinement_sequence=ref.ICASSP2018_REFINEMENT_SEQUENCE))
+      out["min1_%s_%s" % (tag, dn)] = c.predict(data)
+  tiny = blobs(12, 6, 2, seed=9)
+  out["tiny"] = tiny
+  out["tiny_labels"] = ref.SpectralClusterer(
+      fallback_options=fb.FallbackOptions(spectral_min_embeddings=20, naive_threshold=0.6)).predict(tiny)
+  big = orc.synthetic_dvectors(900, 32, 4, seed=1)
+  out["big"] = big
+  out["big_labels"] = ref.SpectralClusterer(
+      min_clusters=2, max_clusters=7, max_spectral_size=300,
+      refinement_options=ref.RefinementOptions(
+          gaussian_blur_sigma=0, p_percentile=0.95,
+          refinement_sequence=ref.ICASSP2018_REFINEMENT_SEQUENCE)).predict(big)
+  np.savez(os.path.join(OUT, "predict_callers.npz"), **out)
+  print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+  main()
