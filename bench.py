@@ -400,7 +400,7 @@ def run_sharded_predict(args, eng, rank, world, dist):
                    "labels_match_generator_truth": True,
                    "clusters_found": clusterer.last_details.get("n_clusters"),
                    "eigensolver": clusterer.last_details.get("solver"),
-                   "lanczos_stats[matvecs,restarts,converged,m]": clusterer.last_details.get("lanczos_stats")},
+                   "lanczos_stats[matvecs,restarts,converged,passes_over_S]": clusterer.last_details.get("lanczos_stats")},
         "e2e": {"value": n * args.steps / e2e_s, "unit": "embeddings/s",
                 "h2d_bytes_per_step": int(x.nbytes) * world, "d2h_bytes_per_step": int(labels.nbytes) * world},
         "gpu_launches": int(launches),
@@ -577,7 +577,7 @@ def main():
                  % (n * n * 4 / 1e9), "parallelism": "replicas x%d" % world,
                  "clusters_found": k_found,
                  "eigensolver": clusterer.last_details.get("solver"),
-                 "lanczos_stats[matvecs,restarts,converged,m]": clusterer.last_details.get("lanczos_stats")},
+                 "lanczos_stats[matvecs,restarts,converged,passes_over_S]": clusterer.last_details.get("lanczos_stats")},
       "e2e": {"value": e2e_value, "unit": "embeddings/s", "h2d_bytes_per_step": int(x.nbytes),
               "d2h_bytes_per_step": int(labels.nbytes) + 8 * 16},
       "gpu_launches": int(launches),

@@ -215,8 +215,9 @@ int sc_memcpy_async(sc_context* ctx, void* dst, const void* src, int64_t bytes, 
  * v_dev, fp64 row-major [n, n_vectors].  SYNCHRONOUS (returns after the stream drains).
  *
  * sc_eigh_dense: Householder tridiagonalisation + implicit QL, all in fp64 on the device, full
- * spectrum (n_values <= n).  sc_eigh_extremal: thick-restart Lanczos on the implicit operator
- * (fp32 S streamed from HBM, fp64 vectors), n_values << n. */
+ * spectrum (n_values <= n).  sc_eigh_extremal: thick-restart block Lanczos on the implicit operator
+ * (fp32 S streamed from HBM once per block of vectors, fp64 vectors), n_values <= 32 << n.
+ * stats_host[4] = {matrix-vector products, restarts, converged pairs, passes over S}. */
 int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t lds, const double* delta,
                   const double* left, const double* right, double sign, int which,
                   int64_t n_values, int64_t n_vectors, double* w_host, double* v_dev,
@@ -226,17 +227,23 @@ int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds, co
                      int64_t n_values, int64_t n_vectors, double tol, int64_t max_matvecs,
                      double* w_host, double* v_dev, int64_t* stats_host, void* stream);
 
-/* Row-sharded variant: `s_block` holds rows [row_begin, row_begin+rows) of S.  Each matvec writes
- * y_full[row_begin .. row_begin+rows) and calls gather(user), which must all-gather y_full across
- * the ranks on `stream` (N doubles per matvec); all other work is replicated, so every rank returns
- * identical results.  delta/left/right and the outputs are full length, as in sc_eigh_extremal. */
-typedef int (*sc_gather_fn)(void* user);
+/* Block size b (vectors multiplied per pass over S) the extremal solver uses for n_values pairs. */
+int sc_eigh_block_size(int64_t n_values);
+
+/* Row-sharded variant: `s_block` holds rows [row_begin, row_begin+rows) of S, and this rank is
+ * slab `slab` of a partition into slabs of `slab_len` rows (row_begin == slab * slab_len).  Every
+ * block product writes b = sc_eigh_block_size(n_values) partial vectors into this rank's slab of
+ * y_slabs, laid out [slab][vector][slab_len] (room for (number of slabs) * b * slab_len doubles),
+ * and calls gather(user, b), which must all-gather the slabs across the ranks on `stream` (b * N
+ * doubles per pass over S); all other work is replicated, so every rank returns identical results.
+ * delta/left/right and the outputs are full length, as in sc_eigh_extremal. */
+typedef int (*sc_gather_fn)(void* user, int count);
 int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, int64_t rows, int64_t row_begin,
                              int64_t n, int64_t lds, const double* delta, const double* left,
                              const double* right, double sign, int which, int64_t n_values,
-                             int64_t n_vectors, double tol, int64_t max_matvecs, double* y_full,
-                             sc_gather_fn gather, void* user, double* w_host, double* v_dev,
-                             int64_t* stats_host, void* stream);
+                             int64_t n_vectors, double tol, int64_t max_matvecs, double* y_slabs,
+                             int slab, int64_t slab_len, sc_gather_fn gather, void* user,
+                             double* w_host, double* v_dev, int64_t* stats_host, void* stream);
 
 /* Rows of e[n,k] (fp64) scaled to unit L2 norm (spectral_clusterer.py:301-305). In place. */
 int sc_row_renorm(sc_context* ctx, double* e, int64_t n, int64_t k, void* stream);

@@ -17,7 +17,7 @@ c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 c_dbl = ctypes.c_double
 c_ptr = ctypes.c_void_p
-GATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)   # sc_gather_fn
+GATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int)   # sc_gather_fn
 
 # name -> argtypes (every function returns int except the two noted); this table is also what
 # tests/test_abi.py checks against include/spectralcluster_b200.h.
@@ -69,9 +69,10 @@ PROTOTYPES = {
                       c_i64, c_ptr, c_ptr, c_ptr],
     "sc_eigh_extremal": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                          c_i64, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sc_eigh_block_size": [c_i64],
     "sc_eigh_extremal_sharded": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
-                                 c_dbl, c_int, c_i64, c_i64, c_dbl, c_i64, c_ptr, c_ptr, c_ptr,
-                                 c_ptr, c_ptr, c_ptr, c_ptr],
+                                 c_dbl, c_int, c_i64, c_i64, c_dbl, c_i64, c_ptr, c_int, c_i64,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "sc_row_renorm": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "sc_kmeans": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_i64, c_dbl,
                   c_ptr, c_ptr, c_ptr],

@@ -1,5 +1,5 @@
-// Extremal symmetric eigensolver for large N: thick-restart Lanczos (symmetric Krylov-Schur)
-// with full re-orthogonalisation, on the implicit operator
+// Extremal symmetric eigensolver for large N: thick-restart BLOCK Lanczos (band form, symmetric
+// block Krylov-Schur) with full re-orthogonalisation, on the implicit operator
 //
 //      Op x = delta .* x + sign * c .* (S (c .* x)),   c = sqrt(left*right)
 //
@@ -9,9 +9,13 @@
 // 4/3 N^3 tridiagonalisation (>= 47 s of HBM traffic at N = 65,536) is replaced by O(100s) of
 // matrix-vector products, each ONE streaming pass over the fp32 matrix S:
 //
-//   k_symv_f32_f64  y = S t : fp32 matrix rows streamed from HBM with 128-bit loads, fp64
-//                   vector staged through shared memory, fp64 accumulation.  4 B/element of
-//                   HBM traffic -- the roofline of this solver is N^2 * 4 B per matvec.
+//   k_symm_f32_f64  Y = S T for a block of b <= 16 vectors: ONE pass over the fp32 matrix per
+//                   block (4 B/element of HBM traffic for b matrix-vector products), fp64 vectors
+//                   staged through shared memory, fp64 accumulation, 4 rows x b vectors of
+//                   register tiling per warp.  A block of b >= (number of wanted pairs) vectors
+//                   also makes the solver find every copy of a repeated eigenvalue (a single
+//                   start vector with full re-orthogonalisation can only ever see one).
+//   k_symv_f32_f64  single-vector variant (kept for b == 1 callers).
 //   k_proj / k_axpy_basis   classical Gram-Schmidt (twice) against the N x m basis
 //   k_combine       thick restart V <- V Z
 // The m x m projected problem is solved on the host by cyclic Jacobi (m <= 128).
@@ -61,24 +65,103 @@ k_symv_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds
   if (row < rows && lane == 0) y[row] = acc;
 }
 
-// t = c .* x
+// Y[p][row] = sum_col S[row][col] * T[p][col], p < P: tall-skinny product with the fp32 matrix read
+// once.  CTA = 8 warps x 4 rows; the T block is staged chunk by chunk in shared memory as
+// [p][col]; lanes walk consecutive columns (coalesced 128 B row segments, conflict-free fp64
+// shared reads); 4 x P fp64 accumulators per lane, reduced across the warp at the end.
+constexpr int SYMM_ROWS_PER_WARP = 4;
+constexpr int SYMM_WARPS = 8;
+constexpr int SYMM_CHUNK = 256;    // columns of T staged per step: P * 256 * 8 B <= 32 KB
+
+template <int P>
+__global__ void __launch_bounds__(SYMM_WARPS * 32)
+k_symm_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
+               const double* __restrict__ t /*[P][n]*/, double* __restrict__ y /*[P][ldy]*/,
+               int64_t ldy) {
+  __shared__ double ts[P][SYMM_CHUNK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * SYMM_WARPS + warp) * SYMM_ROWS_PER_WARP;
+  const float* r[SYMM_ROWS_PER_WARP];
+#pragma unroll
+  for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q) r[q] = s + (row0 + q < rows ? row0 + q : 0) * lds;
+  double acc[SYMM_ROWS_PER_WARP][P];
+#pragma unroll
+  for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[q][p] = 0.0;
+  for (int64_t c0 = 0; c0 < n; c0 += SYMM_CHUNK) {
+    const int64_t len = (n - c0 < SYMM_CHUNK) ? (n - c0) : SYMM_CHUNK;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < P * SYMM_CHUNK; idx += SYMM_WARPS * 32) {
+      const int p = idx / SYMM_CHUNK, j = idx - p * SYMM_CHUNK;
+      ts[p][j] = (j < len) ? t[(int64_t)p * n + c0 + j] : 0.0;
+    }
+    __syncthreads();
+    if (row0 < rows) {
+#pragma unroll 2
+      for (int j = lane; j < SYMM_CHUNK; j += 32) {
+        float q4[SYMM_ROWS_PER_WARP];
+#pragma unroll
+        for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
+          q4[q] = (j < len) ? ld_stream1(r[q] + c0 + j) : 0.0f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const double tv = ts[p][j];                      // zero past len
+#pragma unroll
+          for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q) acc[q][p] = fma((double)q4[q], tv, acc[q][p]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const double v = warp_sum(acc[q][p]);
+      if (lane == 0 && row0 + q < rows) y[(int64_t)p * ldy + row0 + q] = v;
+    }
+}
+
+static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t lds, const double* t,
+                       double* y, int64_t ldy, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + SYMM_WARPS * SYMM_ROWS_PER_WARP - 1) /
+                                   (SYMM_WARPS * SYMM_ROWS_PER_WARP));
+  switch (p) {
+    case 4: k_symm_f32_f64<4><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
+    case 8: k_symm_f32_f64<8><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
+    case 12: k_symm_f32_f64<12><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
+    case 16: k_symm_f32_f64<16><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
+    default: set_error("sc_eigh_extremal: unsupported block size %d", p); return 2;
+  }
+  sc::launched();
+  return 0;
+}
+
+// t_p = c .* x_p for the vectors p = blockIdx.y of a block (contiguous, stride n)
 __global__ void k_prescale(const double* __restrict__ x, const double* __restrict__ left,
                            const double* __restrict__ right, int64_t n, double* __restrict__ t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int64_t o = (int64_t)blockIdx.y * n + i;
   const double c = sqrt((left ? left[i] : 1.0) * (right ? right[i] : 1.0));
-  t[i] = c * x[i];
+  t[o] = c * x[o];
 }
 
-// w = flip * (delta .* x + sign * c .* y)
+// w_p = flip * (delta .* x_p + sign * c .* y_p).  The products are stored in slabs of `slab_len`
+// rows, [slab][vector][slab_len] (one slab per rank when the matrix is row-sharded; a single slab
+// of n rows otherwise): element i of vector p sits at (i / slab_len) * nb * slab_len + p * slab_len
+// + i % slab_len.
 __global__ void k_postscale(const double* __restrict__ x, const double* __restrict__ y,
-                            const double* __restrict__ delta, const double* __restrict__ left,
-                            const double* __restrict__ right, double sign, double flip, int64_t n,
-                            double* __restrict__ w) {
+                            int64_t slab_len, int nb, const double* __restrict__ delta,
+                            const double* __restrict__ left, const double* __restrict__ right,
+                            double sign, double flip, int64_t n, double* __restrict__ w) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int p = blockIdx.y;
+  const int64_t o = (int64_t)p * n + i;
+  const int64_t yi = (i / slab_len) * nb * slab_len + (int64_t)p * slab_len + i % slab_len;
   const double c = sqrt((left ? left[i] : 1.0) * (right ? right[i] : 1.0));
-  w[i] = flip * ((delta ? delta[i] * x[i] : 0.0) + sign * c * y[i]);
+  w[o] = flip * ((delta ? delta[i] * x[o] : 0.0) + sign * c * y[yi]);
 }
 
 // h[j] = <V_j, w>, one CTA per basis vector (deterministic tree reduction)
@@ -166,66 +249,145 @@ __global__ void k_mapback(const double* __restrict__ u, int64_t n, int n_out,
   }
 }
 
-// Cyclic Jacobi for a dense symmetric m x m matrix (row-major, destroyed); eigenvalues in w,
-// eigenvectors in the columns of z.
-static void jacobi_eigh(std::vector<double>& a, int m, std::vector<double>& w,
-                        std::vector<double>& z) {
-  z.assign((size_t)m * m, 0.0);
-  for (int i = 0; i < m; ++i) z[(size_t)i * m + i] = 1.0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < m; ++i) {
-      diag += a[(size_t)i * m + i] * a[(size_t)i * m + i];
-      for (int j = i + 1; j < m; ++j) off += a[(size_t)i * m + j] * a[(size_t)i * m + j];
-    }
-    if (off <= 1e-30 * (diag + off) || off == 0.0) break;
-    for (int p = 0; p < m - 1; ++p) {
-      for (int q = p + 1; q < m; ++q) {
-        const double apq = a[(size_t)p * m + q];
-        if (apq == 0.0) continue;
-        const double app = a[(size_t)p * m + p], aqq = a[(size_t)q * m + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < m; ++k) {          // columns p, q
-          const double akp = a[(size_t)k * m + p], akq = a[(size_t)k * m + q];
-          a[(size_t)k * m + p] = c * akp - s * akq;
-          a[(size_t)k * m + q] = s * akp + c * akq;
+// Host eigensolver of the small projected matrix (m <= 128): Householder tridiagonalisation with
+// accumulated reflectors, then implicit-shift QL (the classic tred2/tql2 pair, O(m^3) with a
+// small constant -- cyclic Jacobi took tens of milliseconds at m = 96).  `a` is row-major and is
+// destroyed; eigenvalues come back ascending in w, eigenvectors in the COLUMNS of z.
+static bool small_eigh(std::vector<double>& a, int m, std::vector<double>& w,
+                       std::vector<double>& z) {
+  std::vector<double> e(m, 0.0);
+  w.assign(m, 0.0);
+  z = a;
+  auto Z = [&](int i, int j) -> double& { return z[(size_t)i * m + j]; };
+  // --- tridiagonalise (rows are annihilated from the last one up)
+  for (int i = m - 1; i > 0; --i) {
+    const int l = i - 1;
+    double h = 0.0, scale = 0.0;
+    if (l > 0) {
+      for (int k = 0; k <= l; ++k) scale += std::fabs(Z(i, k));
+      if (scale == 0.0) {
+        e[i] = Z(i, l);
+      } else {
+        for (int k = 0; k <= l; ++k) {
+          Z(i, k) /= scale;
+          h += Z(i, k) * Z(i, k);
         }
-        for (int k = 0; k < m; ++k) {          // rows p, q
-          const double apk = a[(size_t)p * m + k], aqk = a[(size_t)q * m + k];
-          a[(size_t)p * m + k] = c * apk - s * aqk;
-          a[(size_t)q * m + k] = s * apk + c * aqk;
+        double f = Z(i, l);
+        const double g = (f >= 0.0) ? -std::sqrt(h) : std::sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        Z(i, l) = f - g;
+        f = 0.0;
+        for (int j = 0; j <= l; ++j) {
+          Z(j, i) = Z(i, j) / h;
+          double g2 = 0.0;
+          for (int k = 0; k <= j; ++k) g2 += Z(j, k) * Z(i, k);
+          for (int k = j + 1; k <= l; ++k) g2 += Z(k, j) * Z(i, k);
+          e[j] = g2 / h;
+          f += e[j] * Z(i, j);
         }
-        for (int k = 0; k < m; ++k) {
-          const double zkp = z[(size_t)k * m + p], zkq = z[(size_t)k * m + q];
-          z[(size_t)k * m + p] = c * zkp - s * zkq;
-          z[(size_t)k * m + q] = s * zkp + c * zkq;
+        const double hh = f / (h + h);
+        for (int j = 0; j <= l; ++j) {
+          const double fj = Z(i, j);
+          const double gj = e[j] - hh * fj;
+          e[j] = gj;
+          for (int k = 0; k <= j; ++k) Z(j, k) -= fj * e[k] + gj * Z(i, k);
         }
       }
+    } else {
+      e[i] = Z(i, l);
     }
+    w[i] = h;
   }
-  w.resize(m);
-  for (int i = 0; i < m; ++i) w[i] = a[(size_t)i * m + i];
+  w[0] = 0.0;
+  e[0] = 0.0;
+  for (int i = 0; i < m; ++i) {                 // accumulate the transformation
+    const int l = i - 1;
+    if (w[i] != 0.0) {
+      for (int j = 0; j <= l; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= l; ++k) g += Z(i, k) * Z(k, j);
+        for (int k = 0; k <= l; ++k) Z(k, j) -= g * Z(k, i);
+      }
+    }
+    w[i] = Z(i, i);
+    Z(i, i) = 1.0;
+    for (int j = 0; j <= l; ++j) Z(j, i) = Z(i, j) = 0.0;
+  }
+  // --- implicit QL on (w, e)
+  for (int i = 1; i < m; ++i) e[i - 1] = e[i];
+  e[m - 1] = 0.0;
+  for (int l = 0; l < m; ++l) {
+    int iter = 0, mm;
+    do {
+      for (mm = l; mm < m - 1; ++mm) {
+        const double dd = std::fabs(w[mm]) + std::fabs(w[mm + 1]);
+        if (std::fabs(e[mm]) <= 2.3e-16 * dd) break;
+      }
+      if (mm != l) {
+        if (++iter > 200) return false;
+        double g = (w[l + 1] - w[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = w[mm] - w[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+        double sn = 1.0, cs = 1.0, pp = 0.0;
+        int i;
+        for (i = mm - 1; i >= l; --i) {
+          double f = sn * e[i];
+          const double bb = cs * e[i];
+          r = std::hypot(f, g);
+          e[i + 1] = r;
+          if (r == 0.0) {
+            w[i + 1] -= pp;
+            e[mm] = 0.0;
+            break;
+          }
+          sn = f / r;
+          cs = g / r;
+          g = w[i + 1] - pp;
+          r = (w[i] - g) * sn + 2.0 * cs * bb;
+          pp = sn * r;
+          w[i + 1] = g + pp;
+          g = cs * r - bb;
+          for (int k = 0; k < m; ++k) {
+            f = Z(k, i + 1);
+            Z(k, i + 1) = sn * Z(k, i) + cs * f;
+            Z(k, i) = cs * Z(k, i) - sn * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        w[l] -= pp;
+        e[l] = g;
+        e[mm] = 0.0;
+      }
+    } while (mm != l);
+  }
+  return true;
 }
 
 }  // namespace sc
 
 using namespace sc;
 
-typedef int (*sc_gather_fn)(void* user);
+typedef int (*sc_gather_fn)(void* user, int count);
 
 // Shared implementation.  Unsharded: rows == n, row_begin == 0, y_ext == NULL.  Row-sharded: `s`
-// holds the rows [row_begin, row_begin+rows) of S; every matvec writes its slice of y_ext (a
-// device fp64 vector the caller owns) and calls `gather` to all-gather y_ext across the ranks
-// (N doubles of traffic per matvec); everything else runs replicated on full-length vectors, so
-// every rank takes identical decisions.
+// holds the rows [row_begin, row_begin+rows) of S and rank `slab` of `slabs`; every block product
+// writes its slab of y_ext -- laid out [slab][vector][slab_len], so that one all-gather of
+// contiguous slabs completes it -- and calls gather(user, b); everything else runs replicated on
+// full-length vectors, so every rank takes identical decisions.
+//
+// Band (block) Lanczos with full re-orthogonalisation.  Basis v_0..v_{J-1}; the operator has been
+// applied to the first P of them ("processed"), J = P + b.  One step multiplies the block
+// v_P..v_{P+b-1} (ONE pass over S), then orthogonalises the b products one at a time against the
+// whole basis (classical Gram-Schmidt, twice), each giving one new basis vector.  T = V^T Op V is
+// banded (plus the arrow left by a thick restart); Ritz pairs come from T[0:P,0:P], their
+// residuals from the coupling rows T[P:P+b, 0:P].
 static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t row_begin,
                         int64_t n, int64_t lds, const double* delta, const double* left,
                         const double* right, double sign, int which, int64_t n_values,
                         int64_t n_vectors, double tol, int64_t max_matvecs, double* y_ext,
-                        sc_gather_fn gather, void* user, double* w_host, double* v_dev,
-                        int64_t* stats_host, void* stream) {
+                        int slab, int64_t slab_len, sc_gather_fn gather, void* user,
+                        double* w_host, double* v_dev, int64_t* stats_host, void* stream) {
   SC_REQUIRE(ctx && s && w_host && n > 0, "sc_eigh_extremal: bad arguments");
   SC_REQUIRE(n_values >= 1 && n_values <= 32 && n_vectors >= 0 && n_vectors <= n_values,
              "sc_eigh_extremal: need 1 <= n_values <= 32 and n_vectors <= n_values");
@@ -233,62 +395,91 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   SC_REQUIRE((reinterpret_cast<uintptr_t>(s) & 15) == 0 && lds % 4 == 0,
              "sc_eigh_extremal: S needs a 16-byte aligned base and lds %% 4 == 0");
   const int nev = (int)n_values;
-  const int m = std::max(2 * nev + 32, 64);          // basis size
+  const int b = sc_eigh_block_size(n_values);
+  const int m = 6 * b;                               // processed vectors before a thick restart
+  const int jmax = m + b;                            // basis capacity
   const int keep_extra = std::max(8, nev / 2);
-  SC_REQUIRE(n >= 4 * (int64_t)m, "sc_eigh_extremal: n=%lld too small for the Lanczos basis "
-             "(%d); use sc_eigh_dense", (long long)n, m);
+  SC_REQUIRE(n >= 2 * (int64_t)jmax, "sc_eigh_extremal: n=%lld too small for the Lanczos basis "
+             "(%d); use sc_eigh_dense", (long long)n, jmax);
   if (tol <= 0) tol = 1e-9;
   if (max_matvecs <= 0) max_matvecs = 20000;
   cudaStream_t st = as_stream(stream);
   const double flip = (which == SC_EIG_LARGEST) ? 1.0 : -1.0;
 
   Scratch vb, vb2, work, small;
-  SC_CUDA(vb.alloc(sizeof(double) * (size_t)(m + 1) * n, st));
-  SC_CUDA(vb2.alloc(sizeof(double) * (size_t)(m + 1) * n, st));
-  SC_CUDA(work.alloc(sizeof(double) * (size_t)n * 3, st));
-  SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * (m + 1) + (m + 1) * 64 + 8), st));
+  SC_CUDA(vb.alloc(sizeof(double) * (size_t)jmax * n, st));
+  SC_CUDA(vb2.alloc(sizeof(double) * (size_t)jmax * n, st));
+  SC_CUDA(work.alloc(sizeof(double) * (size_t)n * (3 * b), st));
+  SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * jmax + 8 + jmax * 64), st));
   double* V = vb.as<double>();
   double* V2 = vb2.as<double>();
-  double* t = work.as<double>();
-  double* y = y_ext ? y_ext : t + n;
-  double* w = t + 2 * n;
-  double* h_dev = small.as<double>();          // [m+1]
-  double* h2_dev = h_dev + (m + 1);            // [m+1]
-  double* nrm_dev = h2_dev + (m + 1);          // [1] (+pad)
-  double* z_dev = nrm_dev + 8;                 // [(m+1) x 64]
+  double* tb = work.as<double>();                  // [b][n] prescaled block
+  double* yb = tb + (size_t)b * n;                 // [b][n] products (unsharded)
+  double* wb = yb + (size_t)b * n;                 // [b][n] Op applied, being orthogonalised
+  double* h_dev = small.as<double>();              // [jmax]
+  double* h2_dev = h_dev + jmax;                   // [jmax]
+  double* nrm_dev = h2_dev + jmax;                 // [1] (+pad)
+  double* z_dev = nrm_dev + 8;                     // [jmax x 64]
+  // where the block product lands and how postscale finds element i of vector p
+  double* y_base = y_ext ? y_ext : yb;
+  const int64_t y_slab_len = y_ext ? slab_len : n;
+  double* y_mine = y_base + (y_ext ? (size_t)slab * b * slab_len : 0);
 
   const unsigned gn = (unsigned)((n + 255) / 256);
-  std::vector<double> T((size_t)(m + 1) * (m + 1), 0.0), hh(m + 1), hh2(m + 1);
-  auto Tat = [&](int i, int j) -> double& { return T[(size_t)i * (m + 1) + j]; };
-
-  // start vector
-  k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull); sc::launched();
-  k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
+  const int ldt = jmax;
+  std::vector<double> T((size_t)ldt * ldt, 0.0), hh(jmax), hh2(jmax);
+  auto Tat = [&](int i, int j) -> double& { return T[(size_t)i * ldt + j]; };
   double nrm2 = 0.0;
-  SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-  SC_CUDA(cudaStreamSynchronize(st));
-  k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V); sc::launched();
-  SC_LAUNCH_CHECK();
-
-  int j = 0;                 // basis vectors V[0..j] valid, T[0..j-1][0..j-1] valid
-  int64_t matvecs = 0, restarts = 0;
-  int converged = 0;
-  int mm = m;                // size of the projected problem behind theta / Z
-  std::vector<double> theta, Z;
-  double beta_last = 0.0;
   uint64_t reseed = 1;
 
-  // Rayleigh-Ritz on the leading sz x sz block of T; Ritz values sorted descending.  Returns how
-  // many of the first nev pairs have residual |beta * Z[sz-1, p]| <= tol * max|theta|.
-  auto ritz = [&](int sz, double beta) -> int {
+  // w (device, length n) <- w orthogonalised twice against V[0..cnt); hh += coefficients; returns
+  // its squared norm in nrm2 (host).  One stream synchronisation.
+  auto orthogonalise = [&](double* w, int cnt, bool want_h) -> int {
+    if (cnt > 0) {
+      k_proj<<<cnt, 256, 0, st>>>(V, n, w, h_dev); sc::launched();
+      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, cnt, h_dev, w); sc::launched();
+      k_proj<<<cnt, 256, 0, st>>>(V, n, w, h2_dev); sc::launched();
+      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, cnt, h2_dev, w); sc::launched();
+    }
+    k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
+    SC_LAUNCH_CHECK();
+    if (want_h && cnt > 0) {
+      SC_CUDA(cudaMemcpyAsync(hh.data(), h_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+      SC_CUDA(cudaMemcpyAsync(hh2.data(), h2_dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    }
+    SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  // V[at] <- a fresh random direction orthogonal to V[0..at)
+  auto random_direction = [&](int at) -> int {
+    double* w = wb;                                  // scratch: callers are done with wb[0]
+    k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull + 7919ull * reseed++); sc::launched();
+    if (int rc = orthogonalise(w, at, false)) return rc;
+    k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V + (size_t)at * n); sc::launched();
+    return 0;
+  };
+
+  // start block: b random orthonormal vectors
+  for (int p = 0; p < b; ++p)
+    if (int rc = random_direction(p)) return rc;
+
+  int P = 0, J = b;
+  int64_t matvecs = 0, restarts = 0, passes = 0;
+  int converged = 0, mm = 0;
+  std::vector<double> theta, Z;
+
+  // Rayleigh-Ritz on T[0:sz,0:sz]; Ritz values sorted descending.  Returns how many of the first
+  // nev pairs have residual |T[sz:sz+b, 0:sz] z| <= tol * max|theta|.
+  auto ritz = [&](int sz) -> int {
     std::vector<double> A((size_t)sz * sz);
     for (int r = 0; r < sz; ++r)
       for (int c = 0; c < sz; ++c) A[(size_t)r * sz + c] = 0.5 * (Tat(r, c) + Tat(c, r));
     std::vector<double> wv, zv;
-    jacobi_eigh(A, sz, wv, zv);
+    if (!small_eigh(A, sz, wv, zv)) return -1;
     std::vector<int> ord(sz);
     std::iota(ord.begin(), ord.end(), 0);
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return wv[a] > wv[b]; });
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return wv[x] > wv[y]; });
     theta.assign(sz, 0.0);
     Z.assign((size_t)sz * sz, 0.0);
     for (int p = 0; p < sz; ++p) {
@@ -300,93 +491,91 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
     for (int p = 0; p < sz; ++p) tmax = std::max(tmax, std::fabs(theta[p]));
     int ok = 0;
     for (int p = 0; p < nev && p < sz; ++p) {
-      if (std::fabs(beta * Z[(size_t)(sz - 1) * sz + p]) <= tol * tmax) ++ok;
+      double r2 = 0.0;
+      for (int i = 0; i < b; ++i) {
+        double acc = 0.0;
+        for (int q = 0; q < sz; ++q) acc += Tat(sz + i, q) * Z[(size_t)q * sz + p];
+        r2 += acc * acc;
+      }
+      if (std::sqrt(r2) <= tol * tmax) ++ok;
       else break;
     }
     return ok;
   };
 
-  bool done = false;
-  while (!done) {
-    for (int i = j; i < m; ++i) {
-      // w = flip * Op V_i
-      k_prescale<<<gn, 256, 0, st>>>(V + (size_t)i * n, left, right, n, t); sc::launched();
-      k_symv_f32_f64<<<(unsigned)((rows + SYMV_ROWS - 1) / SYMV_ROWS), SYMV_ROWS * 32, 0, st>>>(
-          s, rows, n, lds, t, y + row_begin); sc::launched();
-      if (gather) {
-        SC_LAUNCH_CHECK();
-        SC_REQUIRE(gather(user) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
-      }
-      k_postscale<<<gn, 256, 0, st>>>(V + (size_t)i * n, y, delta, left, right, sign, flip, n, w); sc::launched();
-      ++matvecs;
-      // classical Gram-Schmidt twice against V_0..V_i
-      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev); sc::launched();
-      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w); sc::launched();
-      k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h2_dev); sc::launched();
-      k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h2_dev, w); sc::launched();
-      k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
-      SC_LAUNCH_CHECK();
-      SC_CUDA(cudaMemcpyAsync(hh.data(), h_dev, sizeof(double) * (i + 1), cudaMemcpyDeviceToHost, st));
-      SC_CUDA(cudaMemcpyAsync(hh2.data(), h2_dev, sizeof(double) * (i + 1), cudaMemcpyDeviceToHost, st));
-      SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-      SC_CUDA(cudaStreamSynchronize(st));
-      for (int q = 0; q <= i; ++q) {
+  for (;;) {
+    // ---- one pass over S: W = flip * Op V[P..P+b)
+    k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb); sc::launched();
+    if (int rc = launch_symm(b, s, rows, n, lds, tb, y_mine, y_slab_len, st)) return rc;
+    SC_LAUNCH_CHECK();
+    if (gather) SC_REQUIRE(gather(user, b) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
+    k_postscale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, y_base, y_slab_len, b, delta, left,
+                                             right, sign, flip, n, wb); sc::launched();
+    matvecs += b;
+    ++passes;
+    // ---- orthogonalise the b products one at a time; each yields one new basis vector
+    for (int p = 0; p < b; ++p) {
+      double* w = wb + (size_t)p * n;
+      const int col = P + p;
+      if (int rc = orthogonalise(w, J, true)) return rc;
+      for (int q = 0; q < J; ++q) {
         const double v = hh[q] + hh2[q];
-        Tat(q, i) = v;
-        Tat(i, q) = v;
+        Tat(q, col) = v;
+        Tat(col, q) = v;
       }
       double beta = std::sqrt(nrm2);
-      const double scale = std::fabs(Tat(i, i)) + 1e-300;
-      if (!(beta > 1e-13 * scale)) {
-        // invariant subspace: continue with a fresh direction orthogonal to the basis
-        k_random_vec<<<gn, 256, 0, st>>>(w, n, 0x5CB200ull + 7919ull * reseed++); sc::launched();
-        for (int pass = 0; pass < 2; ++pass) {
-          k_proj<<<i + 1, 256, 0, st>>>(V, n, w, h_dev); sc::launched();
-          k_axpy_basis<<<gn, 256, 0, st>>>(V, n, i + 1, h_dev, w); sc::launched();
-        }
-        k_norm2<<<1, 1024, 0, st>>>(w, n, nrm_dev); sc::launched();
-        SC_CUDA(cudaMemcpyAsync(&nrm2, nrm_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-        SC_CUDA(cudaStreamSynchronize(st));
-        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / std::sqrt(nrm2), V + (size_t)(i + 1) * n); sc::launched();
+      double scale = std::fabs(Tat(col, col));
+      for (int q = 0; q < J; ++q) scale = std::max(scale, std::fabs(Tat(q, col)));
+      if (!(beta > 1e-12 * (scale + 1e-300))) {
+        // the product lies in the span of the basis (an invariant subspace is complete, or an
+        // eigenvalue is repeated more often than the block is wide): continue with a fresh
+        // direction, coupled to nothing
+        if (int rc = random_direction(J)) return rc;
         beta = 0.0;
       } else {
-        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / beta, V + (size_t)(i + 1) * n); sc::launched();
+        k_scale_into<<<gn, 256, 0, st>>>(w, n, 1.0 / beta, V + (size_t)J * n); sc::launched();
       }
-      Tat(i + 1, i) = beta;
-      Tat(i, i + 1) = beta;
-      beta_last = beta;
-      // early exit: test the Ritz pairs of the growing basis every 8 steps
-      const int sz = i + 1;
-      if (sz < m && sz >= 2 * nev && sz % 8 == 0) {
-        converged = ritz(sz, beta);
-        if (converged >= nev) { done = true; break; }
-      }
+      Tat(J, col) = beta;
+      Tat(col, J) = beta;
+      ++J;
     }
-    if (done) break;
-    converged = ritz(m, beta_last);
+    P += b;
+    converged = ritz(P);
+    SC_REQUIRE(converged >= 0, "sc_eigh_extremal: the projected eigenproblem did not converge");
     if (converged >= nev || matvecs >= max_matvecs) break;
-    // thick restart: keep the leading `keep` Ritz vectors (all converged + a buffer)
-    int keep = std::min(m - 8, nev + keep_extra);
-    std::vector<double> zk((size_t)m * 64, 0.0);
-    SC_REQUIRE(keep <= 64, "sc_eigh_extremal: internal (keep > 64)");
-    for (int q = 0; q < m; ++q)
-      for (int p = 0; p < keep; ++p) zk[(size_t)q * 64 + p] = Z[(size_t)q * m + p];
-    SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)m * 64,
-                            cudaMemcpyHostToDevice, st));
-    k_combine<<<dim3(gn, (unsigned)((keep + 7) / 8)), 256, 0, st>>>(V, n, m, z_dev, 64, keep, V2); sc::launched();
-    SC_CUDA(cudaMemcpyAsync(V2 + (size_t)keep * n, V + (size_t)m * n, sizeof(double) * (size_t)n,
-                            cudaMemcpyDeviceToDevice, st));
-    SC_CUDA(cudaStreamSynchronize(st));      // zk lives on the host stack frame
-    std::swap(V, V2);
-    std::fill(T.begin(), T.end(), 0.0);
-    for (int p = 0; p < keep; ++p) {
-      Tat(p, p) = theta[p];
-      const double cpl = beta_last * Z[(size_t)(m - 1) * m + p];
-      Tat(keep, p) = cpl;
-      Tat(p, keep) = cpl;
+    if (P + b > m) {
+      // ---- thick restart: keep the leading Ritz vectors and the unprocessed block
+      const int keep = std::min(m - b, nev + keep_extra);
+      SC_REQUIRE(keep <= 64 && keep < P, "sc_eigh_extremal: internal (restart size)");
+      std::vector<double> zk((size_t)P * 64, 0.0);
+      for (int q = 0; q < P; ++q)
+        for (int p = 0; p < keep; ++p) zk[(size_t)q * 64 + p] = Z[(size_t)q * P + p];
+      SC_CUDA(cudaMemcpyAsync(z_dev, zk.data(), sizeof(double) * (size_t)P * 64,
+                              cudaMemcpyHostToDevice, st));
+      k_combine<<<dim3(gn, (unsigned)((keep + 7) / 8)), 256, 0, st>>>(V, n, P, z_dev, 64, keep, V2); sc::launched();
+      SC_CUDA(cudaMemcpyAsync(V2 + (size_t)keep * n, V + (size_t)P * n, sizeof(double) * (size_t)n * b,
+                              cudaMemcpyDeviceToDevice, st));
+      SC_CUDA(cudaStreamSynchronize(st));      // zk lives on the host stack frame
+      std::swap(V, V2);
+      // coupling of the unprocessed block to the kept Ritz vectors: C = T[P:P+b, 0:P] Z[:, :keep]
+      std::vector<double> C((size_t)b * keep, 0.0);
+      for (int i = 0; i < b; ++i)
+        for (int p = 0; p < keep; ++p) {
+          double acc = 0.0;
+          for (int q = 0; q < P; ++q) acc += Tat(P + i, q) * Z[(size_t)q * P + p];
+          C[(size_t)i * keep + p] = acc;
+        }
+      std::fill(T.begin(), T.end(), 0.0);
+      for (int p = 0; p < keep; ++p) Tat(p, p) = theta[p];
+      for (int i = 0; i < b; ++i)
+        for (int p = 0; p < keep; ++p) {
+          Tat(keep + i, p) = C[(size_t)i * keep + p];
+          Tat(p, keep + i) = C[(size_t)i * keep + p];
+        }
+      P = keep;
+      J = keep + b;
+      ++restarts;
     }
-    j = keep;
-    ++restarts;
   }
   for (int p = 0; p < nev; ++p) w_host[p] = flip * theta[p];
   if (n_vectors > 0) {
@@ -405,11 +594,15 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
     stats_host[0] = matvecs;
     stats_host[1] = restarts;
     stats_host[2] = converged;
-    stats_host[3] = m;
+    stats_host[3] = passes;
   }
   SC_REQUIRE(converged >= nev, "sc_eigh_extremal: only %d of %d eigenpairs converged to %g in "
              "%lld matrix-vector products", converged, nev, tol, (long long)matvecs);
   return 0;
+}
+
+extern "C" int sc_eigh_block_size(int64_t n_values) {
+  return n_values <= 4 ? 4 : (n_values <= 8 ? 8 : (n_values <= 12 ? 12 : 16));
 }
 
 extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds,
@@ -418,7 +611,7 @@ extern "C" int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int6
                                 double tol, int64_t max_matvecs, double* w_host, double* v_dev,
                                 int64_t* stats_host, void* stream) {
   return lanczos_impl(ctx, s, n, 0, n, lds, delta, left, right, sign, which, n_values, n_vectors,
-                      tol, max_matvecs, nullptr, nullptr, nullptr, w_host, v_dev, stats_host,
+                      tol, max_matvecs, nullptr, 0, 0, nullptr, nullptr, w_host, v_dev, stats_host,
                       stream);
 }
 
@@ -427,12 +620,15 @@ extern "C" int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, i
                                         const double* delta, const double* left,
                                         const double* right, double sign, int which,
                                         int64_t n_values, int64_t n_vectors, double tol,
-                                        int64_t max_matvecs, double* y_full, sc_gather_fn gather,
-                                        void* user, double* w_host, double* v_dev,
-                                        int64_t* stats_host, void* stream) {
-  SC_REQUIRE(s_block && y_full && gather && rows > 0 && row_begin >= 0 && row_begin + rows <= n,
+                                        int64_t max_matvecs, double* y_slabs, int slab,
+                                        int64_t slab_len, sc_gather_fn gather, void* user,
+                                        double* w_host, double* v_dev, int64_t* stats_host,
+                                        void* stream) {
+  SC_REQUIRE(s_block && y_slabs && gather && rows > 0 && row_begin >= 0 && row_begin + rows <= n,
              "sc_eigh_extremal_sharded: bad arguments");
+  SC_REQUIRE(slab >= 0 && slab_len > 0 && row_begin == (int64_t)slab * slab_len && rows <= slab_len,
+             "sc_eigh_extremal_sharded: rank `slab` must own rows [slab*slab_len, +rows)");
   return lanczos_impl(ctx, s_block, rows, row_begin, n, lds, delta, left, right, sign, which,
-                      n_values, n_vectors, tol, max_matvecs, y_full, gather, user, w_host, v_dev,
-                      stats_host, stream);
+                      n_values, n_vectors, tol, max_matvecs, y_slabs, slab, slab_len, gather, user,
+                      w_host, v_dev, stats_host, stream);
 }

@@ -221,7 +221,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
                int diag_shift, unsigned int* __restrict__ pace, int pace_kb,
                float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum,
-               float* __restrict__ mirror, int64_t ldm) {
+               float* __restrict__ mirror_out, int64_t ldm) {
   constexpr bool SPLIT = PREC >= 2;
   constexpr int STAGES = StageGeom<PREC>::STAGES;
   constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
@@ -409,18 +409,37 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
       // ---- write-out.  Each thread holds one row x 128 columns; stored straight from registers
       // that is 16 B per lane into 32 different rows.  Instead every 32x32 block goes through a
       // per-warp staging buffer (float4 granules XOR-swizzled by row: conflict-free both ways) and
-      // leaves as 128-byte row segments, 4 rows per store instruction.
+      // leaves as 128-byte row segments, 4 rows per store instruction.  The same staged block
+      // serves the column reductions of the mirrored half (lane = column: 32 conflict-free
+      // shared loads instead of 5 shuffles per column).  The instruction count matters: at
+      // K = d = 256 (affinity) the epilogue IS the kernel, and a fully unrolled shuffle version
+      // (13 k instructions, 200 KB of code) ran at 1 TB/s.
       const int64_t row_base = (int64_t)tc.m_blk * BM + quad * 32;
       const int64_t row = row_base + lane;
       const int64_t col0 = (int64_t)tc.n_blk * BN + half * 128;
-      float rmax = 0.0f;
+      const bool full = (row_base + 32 <= M) && (col0 + 128 <= N);       // warp-uniform
+      const int rows_valid = (int)min((int64_t)32, max((int64_t)0, (int64_t)M - row_base));
+      // mirror into the tiles that were skipped: target (col, row) lies in tile (col/128, row/256),
+      // which is skipped iff col/128 >= 2 (row/256) + 2.  col0 is a multiple of 128, so the
+      // decision is uniform over the warp's 32 x 128 block; such a block never meets the diagonal.
+      const bool mirror = SYM && (col0 / BM) >= 2 * (row_base / BN) + 2;
       if (EPI == TC_EPI_AFFINITY) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          sum[i] = (sum[i] + 1.0f) * 0.5f;                 // utils.py:39
-          if (col0 + i != row + diag_shift && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
+        for (int i = 0; i < 128; ++i) sum[i] = fmaf(sum[i], 0.5f, 0.5f);   // (x + 1) / 2, utils.py:39
+        if (rowmax_offdiag) {
+          float rmax = 0.0f;
+          const int64_t dcol = row + diag_shift;             // this row's diagonal column
+          const bool no_diag = (row_base + diag_shift + 32 <= col0) || (row_base + diag_shift >= col0 + 128);
+          if (full && no_diag) {
+#pragma unroll
+            for (int i = 0; i < 128; ++i) rmax = fmaxf(rmax, sum[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 128; ++i)
+              if (col0 + i != dcol && col0 + i < N) rmax = fmaxf(rmax, sum[i]);
+          }
+          if (row < M) atomic_max_nonneg(rowmax_offdiag + row, rmax);
         }
-        if (row < M && rowmax_offdiag) atomic_max_nonneg(rowmax_offdiag + row, rmax);
       }
       if (EPI == TC_EPI_PLAIN && stat_rowmax) {
         // fused RowWiseNormalize / degree reductions (refinement.py:243, laplacian.py:41): columns
@@ -439,6 +458,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
       {
         float* stg = store_stage + (warp - 4) * 1024;
         const int sr = lane >> 3, sq = lane & 7;             // store phase: row sr of 4, granule sq
+        const bool col_stats = mirror && ((EPI == TC_EPI_AFFINITY && rowmax_offdiag != nullptr) ||
+                                          (EPI == TC_EPI_PLAIN && stat_rowmax != nullptr));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           __syncwarp();
@@ -449,68 +470,80 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                             sum[c * 32 + 4 * q + 3]);
           __syncwarp();
           const int64_t col = col0 + c * 32 + sq * 4;
+          float* dst = C + (row_base + sr) * ldc + col;
+          if (full) {
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int r = rr * 4 + sr;
-            const float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((sq ^ (r & 7)) << 2));
-            if (row_base + r < M) {
-              float* dst = C + (row_base + r) * ldc + col;
-              if (col + 3 < N) {
-                *reinterpret_cast<float4*>(dst) = v;
+            for (int rr = 0; rr < 8; ++rr) {
+              const int r = rr * 4 + sr;
+              *reinterpret_cast<float4*>(dst + (int64_t)rr * 4 * ldc) =
+                  *reinterpret_cast<const float4*>(stg + r * 32 + ((sq ^ (r & 7)) << 2));
+            }
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int r = rr * 4 + sr;
+              const float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((sq ^ (r & 7)) << 2));
+              if (r < rows_valid) {
+                float* d = dst + (int64_t)rr * 4 * ldc;
+                if (col + 3 < N) {
+                  *reinterpret_cast<float4*>(d) = v;
+                } else {
+                  if (col < N) d[0] = v.x;
+                  if (col + 1 < N) d[1] = v.y;
+                  if (col + 2 < N) d[2] = v.z;
+                }
+              }
+            }
+          }
+          if (col_stats) {
+            // lane = column c*32 + lane of the block; the mirrored elements of that column form a
+            // piece of ROW col0 + c*32 + lane of C.  Rows past M hold 0 (plain) or 0.5 (affinity)
+            // and are skipped.
+            float mx = 0.0f, sm = 0.0f;
+            const int g = lane >> 2, w4 = lane & 3;
+            for (int r = 0; r < rows_valid; ++r) {
+              const float x = stg[r * 32 + ((g ^ (r & 7)) << 2) + w4];
+              mx = fmaxf(mx, x);
+              sm += x;
+            }
+            const int64_t tr = col0 + c * 32 + lane;
+            if (tr < N) {
+              if (EPI == TC_EPI_AFFINITY) {
+                atomic_max_nonneg(rowmax_offdiag + tr, mx);
               } else {
-                if (col < N) dst[0] = v.x;
-                if (col + 1 < N) dst[1] = v.y;
-                if (col + 2 < N) dst[2] = v.z;
+                atomic_max_nonneg(stat_rowmax + tr, mx);
+                atomicAdd(stat_rowsum + tr, (double)sm);
               }
             }
           }
         }
       }
-      if (!SYM && mirror != nullptr && row < M) {
-        // Row-sharded Diffuse: S(g,p) = Y_g Y_p^T is also S(p,g)^T.  `mirror` is rank p's row
+      if (!SYM && mirror_out != nullptr && row < M) {
+        // Row-sharded Diffuse: S(g,p) = Y_g Y_p^T is also S(p,g)^T.  `mirror_out` is rank p's row
         // block of S mapped into this process (CUDA IPC over NVLink): the transposed tile is
         // stored there straight from the accumulator registers -- the exchange step of the
         // sharded product rides on the GEMM epilogue, tile by tile, instead of a separate
         // transpose + send/recv after the last product.  Lanes hold consecutive rows, so every
         // store instruction writes 128 contiguous bytes of one peer row.
+        float* dst = mirror_out + col0 * ldm + row;
+        if (col0 + 128 <= N) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (col0 + i < N) mirror[(col0 + i) * ldm + row] = sum[i];
+          for (int i = 0; i < 128; ++i) dst[(int64_t)i * ldm] = sum[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (col0 + i < N) dst[(int64_t)i * ldm] = sum[i];
+        }
       }
-      if (SYM) {
-        // mirror into the tiles that were skipped: target (col, row) lies in tile
-        // (col/128, row/256), which is skipped iff col/128 >= 2 (row/256) + 2.  col0 is a
-        // multiple of 128, so the decision is uniform over this thread's 128 columns.
-        const bool mirror = (col0 / BM) >= 2 * (row_base / BN) + 2;
-        if (mirror) {
-          if (row < M) {
+      if (mirror && row < M) {
+        float* dst = C + col0 * ldc + row;                 // lanes -> consecutive rows
+        if (col0 + 128 <= N) {
 #pragma unroll
-            for (int i = 0; i < 128; ++i)
-              if (col0 + i < N) C[(col0 + i) * ldc + row] = sum[i];   // lanes -> consecutive rows
-          }
-          // the mirrored elements belong to rows col0 .. col0+127 of C: their reductions run
-          // across the lanes (rows >= M hold zeros / 0.5 and are masked)
-          if (EPI == TC_EPI_AFFINITY && rowmax_offdiag) {
+          for (int i = 0; i < 128; ++i) dst[(int64_t)i * ldc] = sum[i];
+        } else {
 #pragma unroll
-            for (int i = 0; i < 128; ++i) {
-              const float v = warp_max(row < M ? sum[i] : 0.0f);     // never on the diagonal
-              if (lane == 0 && col0 + i < N) atomic_max_nonneg(rowmax_offdiag + col0 + i, v);
-            }
-          }
-          if (EPI == TC_EPI_PLAIN && stat_rowmax) {
-#pragma unroll
-            for (int i = 0; i < 128; ++i) {
-              const float x = row < M ? sum[i] : 0.0f;
-              const float mx = warp_max(x);
-              float sm = x;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-              if (lane == 0 && col0 + i < N) {
-                atomic_max_nonneg(stat_rowmax + col0 + i, mx);
-                atomicAdd(stat_rowsum + col0 + i, (double)sm);
-              }
-            }
-          }
+          for (int i = 0; i < 128; ++i)
+            if (col0 + i < N) dst[(int64_t)i * ldc] = sum[i];
         }
       }
     }

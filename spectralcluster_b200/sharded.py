@@ -614,12 +614,16 @@ def predict_sharded(clusterer, embeddings, dist=None, group=None) -> np.ndarray:
   w = np.empty(limit, dtype=np.float64)
   v = t.empty((n, n_vectors), dtype=t.float64, device=eng.device)
   stats = np.zeros(4, dtype=np.int64)
-  y_full = t.zeros((length,), dtype=t.float64, device=eng.device)
+  # block products land in slabs [rank][vector][block]: one all-gather of contiguous slabs per
+  # pass over S completes all b vectors on every rank
+  width = int(nat.load().sc_eigh_block_size(limit))
+  y_slabs = t.zeros((world * width * plan.block,), dtype=t.float64, device=eng.device)
 
-  def gather(_user):
+  def gather(_user, count):
     try:
       if world > 1:
-        dist.all_gather_into_tensor(y_full, y_full[rank * plan.block:(rank + 1) * plan.block].clone(),
+        per = count * plan.block
+        dist.all_gather_into_tensor(y_slabs[:world * per], y_slabs[rank * per:(rank + 1) * per].clone(),
                                     group=group)
       return 0
     except Exception:                                  # never unwind through the C frame
@@ -629,9 +633,9 @@ def predict_sharded(clusterer, embeddings, dist=None, group=None) -> np.ndarray:
   s_block = res["s_block"]
   eng.call("sc_eigh_extremal_sharded", dev._ptr(s_block), plan.rows, plan.row_begin, n,
            s_block.stride(0), dev._ptr(delta), dev._ptr(left), dev._ptr(right), float(sign),
-           int(which), limit, n_vectors, 1e-9, 0, dev._ptr(y_full), callback, None,
-           w.ctypes.data_as(ctypes.c_void_p), dev._ptr(v), stats.ctypes.data_as(ctypes.c_void_p),
-           eng.stream)
+           int(which), limit, n_vectors, 1e-9, 0, dev._ptr(y_slabs), rank, plan.block, callback,
+           None, w.ctypes.data_as(ctypes.c_void_p), dev._ptr(v),
+           stats.ctypes.data_as(ctypes.c_void_p), eng.stream)
   descend = which == nat.EIG_LARGEST
   if descend:
     k, gap = utils.compute_number_of_clusters(

