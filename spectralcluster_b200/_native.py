@@ -43,6 +43,10 @@ PROTOTYPES = {
     "sc_blur_threshold_symmetrize": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_dbl,
                                      c_dbl, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr,
                                      c_i64, c_ptr],
+    "sc_blur_upper_rowmax": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_int, c_ptr, c_i64, c_ptr,
+                             c_ptr],
+    "sc_threshold_symmetrize_upper": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_dbl, c_int, c_int,
+                                      c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_split_planes": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_diffuse": [c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64,
                    c_ptr, c_ptr, c_ptr],

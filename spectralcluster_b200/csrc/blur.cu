@@ -9,6 +9,15 @@
 //   EPI_STORE materialises B for the generic (unfused) operator API.
 // The blur is recomputed rather than stored: 18 FMAs per element are free next to 4+4 bytes.
 //
+// Whole-matrix, symmetric input (the single-GPU hot path) goes one step further (EPI_UPPER +
+// k_thrsym_upper): B = blur(A) is symmetric, so only the tiles that touch the upper triangle are
+// blurred -- ONCE.  Pass 1 reads half of A, stores that half of B and folds both the row maxima
+// and the column maxima of every tile into m (m_i = max_j B_ij needs the lower half only through
+// B_ji).  Pass 2 is element-wise on the stored half of B and writes Y(i,j) and Y(j,i) (transposed
+// through shared memory).  HBM traffic 2 + 2 + 2 + 4 = 10 B per element of the matrix (the
+// contract figure is 12) and half the filter arithmetic of the two-pass form; both kernels were
+// issue-bound, not bandwidth-bound.
+//
 // Two kernels: k_blur_tile<R> (compile-time radius, register sliding windows; R=4 is sigma=1,
 // the configuration every BASELINE config uses) and k_blur_generic (run-time radius <= 64).
 #include "common.cuh"
@@ -47,7 +56,7 @@ struct BlurWeights {
   float w[2 * kMaxRadius + 1];
 };
 
-enum { EPI_STORE = 0, EPI_STATS = 1, EPI_THRSYM = 2 };
+enum { EPI_STORE = 0, EPI_STATS = 1, EPI_THRSYM = 2, EPI_UPPER = 3 };
 
 // scipy 'reflect' (half-sample symmetric, period 2n): d c b a | a b c d | d c b a
 __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
@@ -166,6 +175,22 @@ __device__ __forceinline__ void epilogue16(const BlurArgs& g, int64_t i, int64_t
     return;
   }
   const int64_t io = i - g.out_row_base;
+  if (EPI == EPI_UPPER) {
+    // edge / diagonal tiles of the symmetric pass: store B, row maximum in the register, column
+    // maxima by one atomic per element (O(N) such tiles out of N^2/4096)
+    float* dst = g.out + io * g.ldo + j0;
+    float v = rmax;
+#pragma unroll
+    for (int t = 0; t < HSTRIP; ++t) {
+      if (!full && j0 + t >= g.n) continue;
+      dst[t] = b[t];
+      const float x = (g.stats_zero_diag && i == j0 + t) ? 0.0f : b[t];
+      v = fmaxf(v, x);
+      atomic_max_nonneg(g.rowmax_out + j0 + t, fmaxf(x, 0.0f));
+    }
+    rmax = v;
+    return;
+  }
   if (EPI == EPI_STORE) {
     float* dst = g.out + io * g.ldo + j0;
     if (full) {
@@ -427,6 +452,49 @@ __device__ __forceinline__ void fast_compute(const BlurArgs& g, const FastCtx<R>
 #pragma unroll
       for (int t = 0; t < HSTRIP; ++t) v = fmaxf(v, b[t]);
       rmax = v;
+    } else if (EPI == EPI_UPPER) {
+#pragma unroll
+      for (int q = 0; q < HSTRIP / 4; ++q)
+        *reinterpret_cast<float4*>(c.out_row + j0 + 4 * q) =
+            make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+      float v = rmax;
+#pragma unroll
+      for (int t = 0; t < HSTRIP; ++t) v = fmaxf(v, b[t]);
+      rmax = v;
+      // Column maxima of the tile: the lanes of this warp are its 32 rows, each holding the same 16
+      // columns.  Halving butterfly: every step a lane hands half of its columns to the partner
+      // and keeps the maxima of the other half -- 16 shuffles in all instead of 80.
+      float u8[8], u4[4], u2[2], u1;
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float mine = (lane & 16) ? b[k + 8] : b[k];
+        const float other = (lane & 16) ? b[k] : b[k + 8];
+        u8[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 16));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float mine = (lane & 8) ? u8[k + 4] : u8[k];
+        const float other = (lane & 8) ? u8[k] : u8[k + 4];
+        u4[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 8));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float mine = (lane & 4) ? u4[k + 2] : u4[k];
+        const float other = (lane & 4) ? u4[k] : u4[k + 2];
+        u2[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 4));
+      }
+      {
+        const float mine = (lane & 2) ? u2[1] : u2[0];
+        const float other = (lane & 2) ? u2[0] : u2[1];
+        u1 = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 2));
+      }
+      u1 = fmaxf(u1, __shfl_xor_sync(0xffffffffu, u1, 1));
+      if ((lane & 1) == 0) {
+        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                        ((lane >> 1) & 1);
+        atomic_max_nonneg(g.rowmax_out + j0 + col, u1);
+      }
     } else if (EPI == EPI_STORE) {
 #pragma unroll
       for (int q = 0; q < HSTRIP / 4; ++q)
@@ -504,7 +572,10 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
   const int64_t row0 = g.row_begin + (int64_t)blockIdx.x * TTH;
   // blockIdx.y selects a run of `tiles_per_cta` column tiles of the band
   const int ntiles = (int)((g.n + TTW - 1) / TTW);
-  const int tx0 = blockIdx.y * g.tiles_per_cta;
+  // EPI_UPPER: only the column tiles that touch the upper triangle of this band
+  const int tx_first = (EPI == EPI_UPPER) ? (int)(row0 / TTW) : 0;
+  const int tx0 = tx_first + blockIdx.y * g.tiles_per_cta;
+  if (tx0 >= ntiles) return;                                   // block-uniform
   const int ntx = min(ntiles, tx0 + g.tiles_per_cta);
 
   // ---- per-thread invariants of the band
@@ -559,7 +630,7 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
     if (tile_is_fast<R>(g, row0, col0)) fast_compute<R, EPI>(g, c, w, col0, cur, mid, rmax);
     else tile_compute<R, EPI>(g, w, row0, col0, cur, mid, rmax);
   }
-  if (EPI == EPI_STATS) {
+  if (EPI == EPI_STATS || EPI == EPI_UPPER) {
     if (threadIdx.x < TTH * (TTW / HSTRIP)) part[threadIdx.x / TTH][threadIdx.x % TTH] = rmax;
     __syncthreads();
     if (threadIdx.x < TTH) {
@@ -568,8 +639,8 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
       for (int s8 = 0; s8 < TTW / HSTRIP; ++s8) v = fmaxf(v, part[s8][threadIdx.x]);
       const int64_t i = row0 + threadIdx.x;
       if (i < g.row_end) {
-        if (gridDim.y == 1) g.rowmax_out[i] = v;
-        else atomic_max_nonneg(g.rowmax_out + i, v);   // few segments per band; caller zero-fills
+        if (EPI == EPI_STATS && gridDim.y == 1) g.rowmax_out[i] = v;
+        else atomic_max_nonneg(g.rowmax_out + i, v);   // caller zero-fills
       }
     }
   }
@@ -588,6 +659,125 @@ __global__ void k_noblur(const BlurArgs g) {
   if (EPI != EPI_THRSYM && g.rowmax_out) {
     vmax = warp_max(fmaxf(vmax, 0.0f));
     if ((threadIdx.x & 31) == 0) atomic_max_nonneg(g.rowmax_out + i, vmax);
+  }
+}
+
+// ------------------------------------------------------------------ symmetric pass 2
+// Element-wise threshold + symmetrize on the stored upper half of B (EPI_UPPER), 64 x 64 tiles
+// with TI <= TJ: y = rule(b, m_i, m_j) is symmetric in (i, j), so the tile is written directly and,
+// for TI < TJ, once more transposed (through shared memory, 128-byte row segments of the planes).
+constexpr int UT = 64;
+
+struct UpperArgs {
+  const float* b;
+  int64_t n, ldb;
+  const float* m;
+  float p, mult;
+  int binarize, preserve_diag, sym_type;
+  float* y;
+  int64_t ldy;
+  __half* hi;
+  __half* lo;
+  int64_t ldh;
+  int tiles;                 // ceil(n / UT)
+};
+
+__device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t j, const float (&y)[4],
+                                         bool full4) {
+  if (full4) {
+    if (g.y) *reinterpret_cast<float4*>(g.y + i * g.ldy + j) = make_float4(y[0], y[1], y[2], y[3]);
+    if (g.hi) {
+      const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y);
+      const __half2 l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
+      *reinterpret_cast<uint2*>(g.hi + i * g.ldh + j) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(g.lo + i * g.ldh + j) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (j + t >= g.n) continue;
+      if (g.y) g.y[i * g.ldy + j + t] = y[t];
+      if (g.hi) {
+        __half h, l;
+        split_half(y[t], h, l);
+        g.hi[i * g.ldh + j + t] = h;
+        g.lo[i * g.ldh + j + t] = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_thrsym_upper(const UpperArgs g) {
+  __shared__ float tile[UT][UT + 1];
+  // linear index -> (TI, TJ) with TI <= TJ: row TI of the triangle starts at TI*T - TI(TI-1)/2
+  const int64_t T = g.tiles, idx = blockIdx.x;
+  int64_t ti = (int64_t)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)idx)) * 0.5);
+  while (ti > 0 && ti * T - ti * (ti - 1) / 2 > idx) --ti;
+  while ((ti + 1) * T - (ti + 1) * ti / 2 <= idx) ++ti;
+  const int64_t tj = ti + (idx - (ti * T - ti * (ti - 1) / 2));
+  const int64_t row0 = ti * UT, col0 = tj * UT;
+  const bool diag_tile = (ti == tj);
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  const int64_t j = col0 + tc;
+  const bool full4 = (j + 3 < g.n);
+  float mj[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (full4) {
+    const float4 v = *reinterpret_cast<const float4*>(g.m + j);
+    mj[0] = v.x; mj[1] = v.y; mj[2] = v.z; mj[3] = v.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) mj[t] = (j + t < g.n) ? g.m[j + t] : 0.0f;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) mj[t] *= g.p;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr + 16 * k;
+    const int64_t i = row0 + r;
+    float y[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (i < g.n) {
+      float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (full4) {
+        const float4 v = ld_stream4(g.b + i * g.ldb + j);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bv[t] = (j + t < g.n) ? g.b[i * g.ldb + j + t] : 0.0f;
+      }
+      const float cut_i = g.m[i] * g.p;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float x = bv[t];
+        const float keep = g.binarize ? 1.0f : x;
+        const float small = x * g.mult;
+        const float t1 = (x < cut_i) ? small : keep;
+        const float t2 = (x < mj[t]) ? small : keep;
+        y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
+        if (g.preserve_diag && diag_tile && i == j + t) y[t] = 1.0f;      // refinement.py:208-209
+      }
+      store_y4(g, i, j, y, full4);
+    }
+    if (!diag_tile) {
+      tile[r][tc] = y[0]; tile[r][tc + 1] = y[1]; tile[r][tc + 2] = y[2]; tile[r][tc + 3] = y[3];
+    }
+  }
+  if (diag_tile) return;                                       // block-uniform
+  __syncthreads();
+  // transposed write: row (col0 + r') of Y, columns row0 + 4 c' .. +3
+  const int64_t jm = row0 + tc;
+  const bool full4m = (jm + 3 < g.n);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr + 16 * k;
+    const int64_t i = col0 + r;
+    if (i >= g.n) continue;
+    const float y[4] = {tile[tc][r], tile[tc + 1][r], tile[tc + 2][r], tile[tc + 3][r]};
+    store_y4(g, i, jm, y, full4m);
   }
 }
 
@@ -777,4 +967,50 @@ extern "C" int sc_blur_threshold_symmetrize_block(
   g.row_begin = row_begin; g.row_end = row_end; g.in_row_base = in_row_base;
   g.out_row_base = row_begin;
   return launch_blur<EPI_THRSYM>(ctx, g, sigma, as_stream(stream));
+}
+
+// ---- symmetric whole-matrix pair (single-GPU hot path).  Pass 1: b_out <- the tiles of blur(a)
+// that touch the upper triangle (the rest of b_out is left untouched), m_out[i] <- max_j blur(a)[i,j]
+// assembled from the row AND column maxima of those tiles.  Requires a symmetric `a` and sigma
+// with radius 4 (sigma in [0.875, 1.125), every BASELINE configuration); the caller falls back to
+// sc_gaussian_blur_rowmax + sc_blur_threshold_symmetrize otherwise.
+extern "C" int sc_blur_upper_rowmax(sc_context* ctx, const float* a, int64_t n, int64_t lda,
+                                    const float* diag_override, double sigma, int zero_diagonal,
+                                    float* b_out, int64_t ldb, float* rowmax_out, void* stream) {
+  SC_REQUIRE(ctx && a && b_out && rowmax_out && n > 0, "sc_blur_upper_rowmax: bad arguments");
+  SC_REQUIRE(sigma > 1e-15 && (int)(4.0 * sigma + 0.5) == 4,
+             "sc_blur_upper_rowmax: the symmetric pass is built for radius 4 (sigma ~ 1)");
+  SC_REQUIRE(n <= 65535LL * 32, "sc_blur_upper_rowmax: n too large for the tile grid");
+  BlurArgs g = {};
+  g.a = a; g.n = n; g.lda = lda; g.diag = diag_override;
+  g.out = b_out; g.ldo = ldb; g.rowmax_out = rowmax_out; g.stats_zero_diag = zero_diagonal;
+  whole_matrix(g);
+  SC_CUDA(cudaMemsetAsync(rowmax_out, 0, sizeof(float) * n, as_stream(stream)));
+  return launch_blur<EPI_UPPER>(ctx, g, sigma, as_stream(stream));
+}
+
+// Pass 2: y / planes <- sym(thr(b, m_i), thr(b, m_j)) for the WHOLE matrix from the upper tiles of b.
+extern "C" int sc_threshold_symmetrize_upper(sc_context* ctx, const float* b, int64_t n, int64_t ldb,
+                                             const float* rowmax, double p, double mult,
+                                             int binarize, int preserve_diagonal, int sym_type,
+                                             float* y, int64_t ldy, void* hi, void* lo, int64_t ldh,
+                                             void* stream) {
+  SC_REQUIRE(ctx && b && rowmax && n > 0, "sc_threshold_symmetrize_upper: bad arguments");
+  SC_REQUIRE(y || (hi && lo), "sc_threshold_symmetrize_upper: no output given");
+  SC_REQUIRE((hi == nullptr) == (lo == nullptr), "hi/lo must come together");
+  SC_REQUIRE(sym_type == SC_SYMMETRIZE_MAX || sym_type == SC_SYMMETRIZE_AVERAGE,
+             "Unsupported symmetrize_type.");
+  SC_REQUIRE(vec_ok_f32(b, ldb) && aligned16(rowmax), "sc_threshold_symmetrize_upper: `b` / rowmax alignment");
+  UpperArgs g = {};
+  g.b = b; g.n = n; g.ldb = ldb; g.m = rowmax; g.p = (float)p; g.mult = (float)mult;
+  g.binarize = binarize; g.preserve_diag = preserve_diagonal; g.sym_type = sym_type;
+  g.y = y; g.ldy = ldy; g.hi = (__half*)hi; g.lo = (__half*)lo; g.ldh = ldh;
+  SC_REQUIRE(!y || vec_ok_f32(y, ldy), "sc_threshold_symmetrize_upper: `y` alignment");
+  SC_REQUIRE(!hi || (vec_ok_f16(hi, ldh) && vec_ok_f16(lo, ldh)), "sc_threshold_symmetrize_upper: plane alignment");
+  g.tiles = (int)((n + UT - 1) / UT);
+  const int64_t pairs = (int64_t)g.tiles * (g.tiles + 1) / 2;
+  SC_REQUIRE(pairs < (1LL << 31), "sc_threshold_symmetrize_upper: n too large for the tile grid");
+  k_thrsym_upper<<<(unsigned)pairs, 256, 0, as_stream(stream)>>>(g); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
 }

@@ -209,6 +209,30 @@ class Engine:
               0 if hi is None else hi.stride(0), self.stream)
     return y, hi, lo
 
+  def blur_upper_rowmax(self, a, n, sigma, diag, zero_diag):
+    """Symmetric pass 1: (b with its upper tiles = blur(a), m = row maxima of blur(a))."""
+    t = torch()
+    b = self.matrix(n)
+    m = self.vector(n, t.float32)
+    self.call("sc_blur_upper_rowmax", _ptr(a), n, a.stride(0), _ptr(diag), float(sigma),
+              int(bool(zero_diag)), _ptr(b), b.stride(0), _ptr(m), self.stream)
+    return b, m
+
+  def threshold_symmetrize_upper(self, b, n, rowmax, p, mult, binarize, preserve_diag, sym_type,
+                                 want_f32, want_planes):
+    y = self.matrix(n) if want_f32 else None
+    hi, lo = self.planes(n) if want_planes else (None, None)
+    self.call("sc_threshold_symmetrize_upper", _ptr(b), n, b.stride(0), _ptr(rowmax), float(p),
+              float(mult), int(bool(binarize)), int(bool(preserve_diag)), int(sym_type), _ptr(y),
+              0 if y is None else y.stride(0), _ptr(hi), _ptr(lo),
+              0 if hi is None else hi.stride(0), self.stream)
+    return y, hi, lo
+
+  @staticmethod
+  def upper_pass_ok(sigma: float) -> bool:
+    """The symmetric blur pair covers radius-4 filters (sigma ~ 1, every BASELINE config)."""
+    return sigma > 1e-15 and int(4.0 * sigma + 0.5) == 4 and os.environ.get("SCB_BLUR_TWO_PASS") != "1"
+
   def split_planes(self, a, n):
     hi, lo = self.planes(n)
     self.call("sc_split_planes", _ptr(a), n, a.stride(0), _ptr(hi), _ptr(lo), hi.stride(0),
@@ -353,16 +377,24 @@ def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetri
         else:
           diag = eng.crop_values(cur, n)
       zero_diag = bool(options.thresholding_preserve_diagonal)
-      m = eng.blur_rowmax(cur, n, sigma, diag, zero_diag)
       next_is_diffuse = j + 2 < len(names) and names[j + 2] == RN.Diffuse
       use_tc = eng.gemm_engine(n) == nat.GEMM_TCGEN05
       want_planes = next_is_diffuse and use_tc
       want_f32 = not want_planes
-      y, hi, lo = eng.blur_threshold_symmetrize(
-          cur, n, sigma, diag, m, options.p_percentile, options.thresholding_soft_multiplier,
-          options.thresholding_with_binarization, zero_diag,
-          nat.SYMMETRIZE_MAX if options.symmetrize_type == rf.SymmetrizeType.Max
-          else nat.SYMMETRIZE_AVERAGE, want_f32, want_planes)
+      sym_type = (nat.SYMMETRIZE_MAX if options.symmetrize_type == rf.SymmetrizeType.Max
+                  else nat.SYMMETRIZE_AVERAGE)
+      if eng.upper_pass_ok(sigma):
+        # blur(A) is symmetric: blur the upper tiles once, keep them, mirror the result
+        b, m = eng.blur_upper_rowmax(cur, n, sigma, diag, zero_diag)
+        y, hi, lo = eng.threshold_symmetrize_upper(
+            b, n, m, options.p_percentile, options.thresholding_soft_multiplier,
+            options.thresholding_with_binarization, zero_diag, sym_type, want_f32, want_planes)
+        del b
+      else:
+        m = eng.blur_rowmax(cur, n, sigma, diag, zero_diag)
+        y, hi, lo = eng.blur_threshold_symmetrize(
+            cur, n, sigma, diag, m, options.p_percentile, options.thresholding_soft_multiplier,
+            options.thresholding_with_binarization, zero_diag, sym_type, want_f32, want_planes)
       cur = y
       planes = (hi, lo) if want_planes else None
       cur_is_planes_only = want_planes

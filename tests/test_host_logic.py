@@ -70,6 +70,17 @@ class FakeEngine:
   def symmetrize(self, a, n, kind): return self._rec("symmetrize", kind)
   def blur_rowmax(self, a, n, sigma, diag, zero_diag): return self._rec("blur_rowmax", sigma, diag)
 
+  def upper_pass_ok(self, sigma):
+    return dev.Engine.upper_pass_ok(sigma)
+
+  def blur_upper_rowmax(self, a, n, sigma, diag, zero_diag):
+    self._rec("blur_upper", sigma, diag)
+    return "B", "m"
+
+  def threshold_symmetrize_upper(self, b, n, m, p, mult, binarize, keep, sym, want_f32, want_planes):
+    self._rec("thrsym_upper", b, m, sym, want_f32, want_planes)
+    return ("y" if want_f32 else None, "hi" if want_planes else None, "lo" if want_planes else None)
+
   def blur_threshold_symmetrize(self, a, n, sigma, diag, m, p, mult, binarize, keep, sym, want_f32,
                                 want_planes):
     self._rec("blur_thrsym", sigma, diag, sym, want_f32, want_planes)
@@ -95,10 +106,11 @@ def test_planner_fuses_the_icassp_sequence():
   eng = FakeEngine(1000)
   opt = scb.RefinementOptions(refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
   out = dev.run_refinement(eng, "A", 1000, opt, crop_vector="cropvec")
+  # sigma = 1: the symmetric blur pair (upper tiles blurred once, result mirrored);
   # RowWiseNormalize's row maxima (and the degree) come out of the Diffuse epilogue: no row_stats
-  assert names(eng) == ["blur_rowmax", "blur_thrsym", "diffuse"]
+  assert names(eng) == ["blur_upper", "thrsym_upper", "diffuse"]
   assert eng.calls[0][1:] == (1.0, "cropvec")            # crop vector from the affinity epilogue
-  assert eng.calls[1][3:] == (nat.SYMMETRIZE_MAX, False, True)   # planes only: Diffuse follows
+  assert eng.calls[1][1:] == ("B", "m", nat.SYMMETRIZE_MAX, False, True)   # planes only: Diffuse follows
   assert eng.calls[2][1:] == (None, "hi", True)          # tensor-core Diffuse on the planes
   assert out.symmetric and torch.allclose(out.row_scale, torch.full((1000,), 0.5, dtype=torch.float64))
   assert torch.allclose(out.rowsum, torch.full((1000,), 3.0, dtype=torch.float64))
@@ -120,6 +132,11 @@ def test_planner_variants():
   dev.run_refinement(eng, "A", 20, opt, crop_vector="c")
   assert eng.calls[1][4:] == (True, False) and eng.calls[2][1:] == ("y", None, False)
   assert names(eng)[-1] == "row_stats"                   # SIMT GEMM: separate reduction pass
+  # a blur radius other than 4 keeps the two-pass form (blur recomputed in both passes)
+  eng = FakeEngine(1000)
+  opt = scb.RefinementOptions(gaussian_blur_sigma=2, refinement_sequence=list(scb.ICASSP2018_REFINEMENT_SEQUENCE))
+  dev.run_refinement(eng, "A", 1000, opt, crop_vector="c")
+  assert names(eng)[:2] == ["blur_rowmax", "blur_thrsym"]
   # Percentile thresholding and threshold-without-symmetrize are not fusable
   eng = FakeEngine(300)
   opt = scb.RefinementOptions(thresholding_type=scb.ThresholdType.Percentile,
