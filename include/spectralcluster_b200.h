@@ -259,6 +259,29 @@ int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, int64_t rows
                              int slab, int64_t slab_len, sc_gather_fn gather, void* user,
                              double* w_host, double* v_dev, int64_t* stats_host, void* stream);
 
+/* ---- Krylov primitives of the general (non-symmetrisable) eigen path: utils.py:59-61 is
+ * np.linalg.eig + .real; sequences such as [RowWiseThreshold] alone leave a genuinely
+ * non-symmetric matrix.  The Krylov-Schur recurrence is host logic
+ * (spectralcluster_b200/arnoldi.py); everything of length n runs here.  Vectors are fp64, basis
+ * vectors contiguous (vector q at v + q*n).
+ *   matvec        y[rows] = a[rows, n] x            (fp32 matrix streamed once, fp64 accumulate)
+ *   orthogonalize w -= V (V^T w) twice; h_host[count] = coefficients, *nrm2_host = |w|^2  (SYNC)
+ *   scale         out = alpha * w
+ *   random        w = a reproducible pseudo-random direction
+ *   combine       out[p] = sum_q z_host[q*k + p] v[q], p < k <= 64                          (SYNC)
+ *   columns       v_out[n, k] row-major <- the k vectors of u, each scaled to unit norm */
+int sc_krylov_matvec(sc_context* ctx, const float* a, int64_t rows, int64_t n, int64_t lda,
+                     const double* x, double* y, void* stream);
+int sc_krylov_orthogonalize(sc_context* ctx, const double* v, int64_t n, int64_t count, double* w,
+                            double* h_host, double* nrm2_host, void* stream);
+int sc_krylov_scale(sc_context* ctx, const double* w, int64_t n, double alpha, double* out,
+                    void* stream);
+int sc_krylov_random(sc_context* ctx, double* w, int64_t n, int64_t seed, void* stream);
+int sc_krylov_combine(sc_context* ctx, const double* v, int64_t n, int64_t m, const double* z_host,
+                      int64_t k, double* out, void* stream);
+int sc_krylov_columns(sc_context* ctx, const double* u, int64_t n, int64_t k, double* v_out,
+                      void* stream);
+
 /* Rows of e[n,k] (fp64) scaled to unit L2 norm (spectral_clusterer.py:301-305). In place. */
 int sc_row_renorm(sc_context* ctx, double* e, int64_t n, int64_t k, void* stream);
 

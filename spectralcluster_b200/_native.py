@@ -77,6 +77,12 @@ PROTOTYPES = {
     "sc_eigh_extremal_sharded": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
                                  c_dbl, c_int, c_i64, c_i64, c_dbl, c_i64, c_ptr, c_int, c_i64,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sc_krylov_matvec": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "sc_krylov_orthogonalize": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sc_krylov_scale": [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr],
+    "sc_krylov_random": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
+    "sc_krylov_combine": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr],
+    "sc_krylov_columns": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr],
     "sc_row_renorm": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "sc_kmeans": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_i64, c_dbl,
                   c_ptr, c_ptr, c_ptr],

@@ -632,3 +632,98 @@ extern "C" int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, i
                       n_values, n_vectors, tol, max_matvecs, y_slabs, slab, slab_len, gather, user,
                       w_host, v_dev, stats_host, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Krylov primitives for the GENERAL (non-symmetrisable) eigen path (SURVEY.md 8(f)-1;
+// utils.py:59-61 is np.linalg.eig + .real).  The N-length work -- products with the fp32 matrix,
+// Gram-Schmidt against the basis, Ritz-vector assembly -- runs here; the Krylov-Schur recurrence
+// itself (a small m x m real Schur form per restart) is host logic in
+// spectralcluster_b200/arnoldi.py.
+extern "C" int sc_krylov_matvec(sc_context* ctx, const float* a, int64_t rows, int64_t n, int64_t lda,
+                                const double* x, double* y, void* stream) {
+  SC_REQUIRE(ctx && a && x && y && rows > 0 && n > 0, "sc_krylov_matvec: bad arguments");
+  k_symv_f32_f64<<<(unsigned)((rows + SYMV_ROWS - 1) / SYMV_ROWS), SYMV_ROWS * 32, 0, as_stream(stream)>>>(
+      a, rows, n, lda, x, y); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+// w <- w - V (V^T w), twice (classical Gram-Schmidt with re-orthogonalisation) against the `count`
+// basis vectors V[0..count) (each of length n, contiguous); h_host[count] receives the summed
+// coefficients, nrm2_host the squared norm of what is left.  SYNCHRONOUS.
+extern "C" int sc_krylov_orthogonalize(sc_context* ctx, const double* v, int64_t n, int64_t count,
+                                       double* w, double* h_host, double* nrm2_host, void* stream) {
+  SC_REQUIRE(ctx && w && nrm2_host && n > 0 && count >= 0 && (count == 0 || (v && h_host)),
+             "sc_krylov_orthogonalize: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  Scratch small;
+  SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * count + 8), st));
+  double* h1 = small.as<double>();
+  double* h2 = h1 + count;
+  double* nrm = h2 + count;
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  std::vector<double> a((size_t)count), b((size_t)count);
+  if (count > 0) {
+    k_proj<<<(unsigned)count, 256, 0, st>>>(v, n, w, h1); sc::launched();
+    k_axpy_basis<<<gn, 256, 0, st>>>(v, n, (int)count, h1, w); sc::launched();
+    k_proj<<<(unsigned)count, 256, 0, st>>>(v, n, w, h2); sc::launched();
+    k_axpy_basis<<<gn, 256, 0, st>>>(v, n, (int)count, h2, w); sc::launched();
+  }
+  k_norm2<<<1, 1024, 0, st>>>(w, n, nrm); sc::launched();
+  SC_LAUNCH_CHECK();
+  if (count > 0) {
+    SC_CUDA(cudaMemcpyAsync(a.data(), h1, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaMemcpyAsync(b.data(), h2, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+  }
+  SC_CUDA(cudaMemcpyAsync(nrm2_host, nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SC_CUDA(cudaStreamSynchronize(st));
+  for (int64_t q = 0; q < count; ++q) h_host[q] = a[q] + b[q];
+  return 0;
+}
+
+extern "C" int sc_krylov_scale(sc_context* ctx, const double* w, int64_t n, double alpha, double* out,
+                               void* stream) {
+  SC_REQUIRE(ctx && w && out && n > 0, "sc_krylov_scale: bad arguments");
+  k_scale_into<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(w, n, alpha, out); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_krylov_random(sc_context* ctx, double* w, int64_t n, int64_t seed, void* stream) {
+  SC_REQUIRE(ctx && w && n > 0, "sc_krylov_random: bad arguments");
+  k_random_vec<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(w, n, 0x5CB200ull + 7919ull * (uint64_t)seed);
+  sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[p] = sum_q z_host[q*k + p] V_q for p < k <= 64 (Ritz vectors / restart basis).  out holds k
+// vectors of length n and must not alias v.  SYNCHRONOUS.
+extern "C" int sc_krylov_combine(sc_context* ctx, const double* v, int64_t n, int64_t m,
+                                 const double* z_host, int64_t k, double* out, void* stream) {
+  SC_REQUIRE(ctx && v && z_host && out && n > 0 && m > 0 && k > 0 && k <= 64 && out != v,
+             "sc_krylov_combine: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  Scratch zs;
+  SC_CUDA(zs.alloc(sizeof(double) * (size_t)m * 64, st));
+  std::vector<double> zk((size_t)m * 64, 0.0);
+  for (int64_t q = 0; q < m; ++q)
+    for (int64_t p = 0; p < k; ++p) zk[(size_t)q * 64 + p] = z_host[(size_t)q * k + p];
+  SC_CUDA(cudaMemcpyAsync(zs.as<double>(), zk.data(), sizeof(double) * (size_t)m * 64,
+                          cudaMemcpyHostToDevice, st));
+  k_combine<<<dim3((unsigned)((n + 255) / 256), (unsigned)((k + 7) / 8)), 256, 0, st>>>(
+      v, n, (int)m, zs.as<double>(), 64, (int)k, out); sc::launched();
+  SC_LAUNCH_CHECK();
+  SC_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// v_out[i, col] = u_col[i] / |u_col|: `k` vectors of length n (contiguous) -> unit-norm columns of
+// a row-major [n, k] array (the layout k-means reads).
+extern "C" int sc_krylov_columns(sc_context* ctx, const double* u, int64_t n, int64_t k, double* v_out,
+                                 void* stream) {
+  SC_REQUIRE(ctx && u && v_out && n > 0 && k > 0, "sc_krylov_columns: bad arguments");
+  k_mapback<<<(unsigned)k, 512, 0, as_stream(stream)>>>(u, n, (int)k, nullptr, nullptr, v_out); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}

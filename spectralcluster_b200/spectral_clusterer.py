@@ -94,11 +94,6 @@ class SpectralClusterer:
                                  crop_vector=affinity.crop_vector,
                                  a_symmetric=affinity.symmetric,
                                  diffuse_precision=eng.diffuse_precision)
-    if not refined.symmetric:
-      raise NotImplementedError(
-          "this refinement sequence leaves a matrix that is not symmetric or diagonally similar "
-          "to a symmetric one; the general eigensolver is outside the B200 hot path "
-          "(SURVEY.md 8(f) rank 1)")
     delta, left, right, sign, which = laplacian_lib.operator_terms(eng, refined,
                                                                    self.laplacian_type)
     descend = which == nat.EIG_LARGEST
@@ -106,6 +101,26 @@ class SpectralClusterer:
     if self.max_clusters and self.max_clusters + 1 < limit:
       limit = self.max_clusters + 1
     n_vectors = min(n, max(limit, self.min_clusters or 0))
+    if not refined.symmetric:
+      # not symmetric nor diagonally similar to a symmetric matrix (e.g. RowWiseThreshold without
+      # Symmetrize): np.linalg.eig + .real semantics (utils.py:59-61) by Krylov-Schur
+      from . import arnoldi
+      w, v, stats = arnoldi.eig_extremal_device(eng, refined.s, n, delta, left, right, sign,
+                                                not descend, limit, n_vectors)
+      if descend:
+        k, gap = utils.compute_number_of_clusters(
+            w, max_clusters=self.max_clusters, stop_eigenvalue=self.stop_eigenvalue,
+            eigengap_type=self.eigengap_type, descend=True)
+      else:
+        if self.eigengap_type == EigenGapType.NormalizedDiff and limit < n:
+          top, _, _ = arnoldi.eig_extremal_device(eng, refined.s, n, delta, left, right, sign,
+                                                  False, 1, 0)
+          w = np.concatenate([w, top])
+        k, gap = utils.compute_number_of_clusters(
+            w, max_clusters=self.max_clusters, eigengap_type=self.eigengap_type, descend=False)
+      self.last_details = dict(eigenvalues=np.array(w[:limit]), n_clusters_raw=k, max_gap=gap,
+                               solver="krylov-schur", lanczos_stats=stats)
+      return w, v, k, gap
     # Lanczos needs a basis of m = max(2*limit+32, 64) vectors and n >= 4 m; it is ~600x faster
     # than the full-spectrum Householder/QL solver at N = 2,048 (3 ms vs 2 s), so the dense solver
     # is kept for small matrices and for max_clusters=None (every eigenvalue is needed).

@@ -104,5 +104,66 @@ def main():
   print("wrote", sorted(os.listdir(OUT)))
 
 
+
+
+
+def nonsymmetric():
+  """sequences that leave a genuinely non-symmetric matrix (np.linalg.eig +
+  .real in the reference, utils.py:59-61): the reference's own auto-tune tests
+  (tests/spectral_clusterer_test.py:156-241) plus two synthetic cases with eigenvalues."""
+  RN = ref.RefinementName
+  six = np.array([[1.0, 0.0], [1.1, 0.1], [0.0, 1.0], [0.1, 1.0], [0.9, -0.1], [0.0, 1.2]])
+  out = {}
+
+  def autotune_clusterer(p_min, p_max, step, max_clusters):
+    return ref.SpectralClusterer(
+        max_clusters=max_clusters,
+        refinement_options=ref.RefinementOptions(
+            thresholding_type=ref.ThresholdType.Percentile,
+            refinement_sequence=[RN.RowWiseThreshold]),
+        autotune=ref.AutoTune(p_percentile_min=p_min, p_percentile_max=p_max,
+                              init_search_step=step, search_level=1),
+        laplacian_type=ref.LaplacianType.GraphCut, row_wise_renorm=True)
+
+  c = autotune_clusterer(0.60, 0.95, 0.05, 2)
+  out["six"] = six
+  out["six_labels"] = c.predict(six)
+  base = np.array([[1.0, 0, 0, 0, 0, 0]] * 400 + [[0, 1.0, 0, 0, 0, 0]] * 300 +
+                  [[0, 0, 2.0, 0, 0, 0]] * 200 + [[0, 0, 0, 1.0, 0, 0]] * 100)
+  x = base + (np.random.RandomState(3).rand(1000, 6) * 2 - 1) * 0.1
+  c = autotune_clusterer(0.9, 0.95, 0.03, 4)
+  out["k1000"] = x
+  out["k1000_labels"] = c.predict(x)
+  out["k1000_p"] = np.array(c.refinement_options.p_percentile)
+  # no autotune: eigenvalues and labels of two non-symmetric pipelines
+  x = orc.synthetic_dvectors(800, 64, 4, seed=5)
+  out["syn"] = x
+  for tag, seq, lap in (("thr_graphcut", [RN.RowWiseThreshold], ref.LaplacianType.GraphCut),
+                        ("blur_thr_none", [RN.GaussianBlur, RN.RowWiseThreshold], None),
+                        ("thr_rw", [RN.CropDiagonal, RN.RowWiseThreshold], ref.LaplacianType.RandomWalk)):
+    c = ref.SpectralClusterer(
+        min_clusters=2, max_clusters=7, laplacian_type=lap,
+        refinement_options=ref.RefinementOptions(
+            gaussian_blur_sigma=1, p_percentile=0.9, thresholding_soft_multiplier=0.01,
+            refinement_sequence=seq))
+    a = utils.compute_affinity_matrix(x)
+    vec, k, gap = c._compute_eigenvectors_ncluster(a)
+    for op in seq:
+      a = c.refinement_options.get_refinement_operator(op).refine(a)
+    if lap is None:
+      w, _ = utils.compute_sorted_eigenvectors(a)
+    else:
+      from spectralcluster import laplacian as lp
+      w, _ = utils.compute_sorted_eigenvectors(lp.compute_laplacian(a, lap), descend=False)
+    out[tag + "_w"] = np.real(w[:8])
+    out[tag + "_k"] = np.array(k)
+    out[tag + "_gap"] = np.array(gap)
+    out[tag + "_labels"] = c.predict(x)
+  np.savez(os.path.join(OUT, "nonsymmetric.npz"), **out)
+  print("nonsymmetric:", {k: (v.shape if v.ndim else v.item()) for k, v in out.items()
+                          if k.endswith(("_k", "_p", "_gap"))})
+
+
 if __name__ == "__main__":
   main()
+  nonsymmetric()
