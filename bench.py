@@ -285,18 +285,18 @@ def run_sharded(args, eng, rank, world, dist):
     dist.destroy_process_group()
 
 
-def dtype_string(eng):
+def dtype_string(eng, n):
   from spectralcluster_b200 import _native as nat
   scheme = {nat.GEMM_SPLIT3: "fp16x3 split (hi*hi + hi*lo + lo*hi)",
             nat.GEMM_SPLIT2: "fp16x2 split ((hi+lo)*hi)",
-            nat.GEMM_SINGLE: "fp16 single (hi*hi)"}[eng.diffuse_precision]
+            nat.GEMM_SINGLE: "fp16 single (hi*hi)"}[eng.diffuse_precision_for(n)]
   return ("f32 storage; affinity: fp16x3 split tcgen05 MMAs; Diffuse: %s tcgen05 MMAs, f32 "
           "two-level accumulate; f64 eigensolve and k-means" % scheme)
 
 
-def mma_per_product(eng):
+def mma_per_product(eng, n):
   from spectralcluster_b200 import _native as nat
-  return {nat.GEMM_SPLIT3: 3, nat.GEMM_SPLIT2: 2, nat.GEMM_SINGLE: 1}[eng.diffuse_precision]
+  return {nat.GEMM_SPLIT3: 3, nat.GEMM_SPLIT2: 2, nat.GEMM_SINGLE: 1}[eng.diffuse_precision_for(n)]
 
 
 def load_peaks():
@@ -392,7 +392,7 @@ def run_sharded_predict(args, eng, rank, world, dist):
         "metric": "embeddings/sec through predict()", "value": n / (per / 1e3),
         "unit": "embeddings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": dtype_string(eng), "data": "synthetic",
+        "vs_baseline": None, "dtype": dtype_string(eng, n), "data": "synthetic",
         "config": {"workload": workload_name(n, d),
                    "l2": "inputs larger than L2 (N x N fp32 = %.1f GB over %d GPUs)" % (n * n * 4 / 1e9, world),
                    "parallelism": "ONE problem, N x N matrices row-sharded x%d (strong scaling)" % world,
@@ -412,7 +412,7 @@ def run_sharded_predict(args, eng, rank, world, dist):
                      "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
                      "note": "achieved = this rank's share of the N^3 triangle-basis flop / CUDA-event "
                              "time of its sc_gemm_nt_planes calls; %d MMAs issued per product"
-                             % mma_per_product(eng)},
+                             % mma_per_product(eng, n)},
         "clocks": sampler.summary()})
   if world > 1:
     dist.destroy_process_group()
@@ -571,7 +571,7 @@ def main():
       "metric": "embeddings/sec through predict()", "value": value, "unit": "embeddings/s",
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
       "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
-      "dtype": dtype_string(eng),
+      "dtype": dtype_string(eng, n),
       "data": "synthetic",
       "config": {"workload": workload_name(n, d), "l2": "inputs larger than L2 (N x N fp32 = %.1f GB)"
                  % (n * n * 4 / 1e9), "parallelism": "replicas x%d" % world,
@@ -592,9 +592,9 @@ def main():
                                       "frac": achieved / 2 / tensor_peak if achieved else None,
                                       "note": "N^3: the kernel computes only the tiles that touch the "
                                               "upper triangle and mirrors them"},
-                   "issued_mma": {"achieved": achieved / 2 * mma_per_product(eng) if achieved else None,
-                                  "frac": achieved / 2 * mma_per_product(eng) / tensor_peak if achieved else None,
-                                  "note": "fp16 MMA flop actually issued = %d x N^3" % mma_per_product(eng)},
+                   "issued_mma": {"achieved": achieved / 2 * mma_per_product(eng, n) if achieved else None,
+                                  "frac": achieved / 2 * mma_per_product(eng, n) / tensor_peak if achieved else None,
+                                  "note": "fp16 MMA flop actually issued = %d x N^3" % mma_per_product(eng, n)},
                    "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse"},
       "roofline_hbm_stages": (lambda t1, t2: {
           "blur_stats_pass_GBps": (n * n * 4 / 1e9) / (t1 / 1e3) if t1 else None,

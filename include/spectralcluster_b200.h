@@ -129,8 +129,9 @@ int sc_blur_threshold_symmetrize(sc_context* ctx, const float* a, int64_t n, int
  * the upper triangle only (blur(a) is symmetric): sc_blur_upper_rowmax stores those tiles of
  * b = blur(a) (the rest of b is left untouched) and assembles rowmax[i] = max_j b[i,j] from their row
  * and column maxima (zero-fills rowmax itself); sc_threshold_symmetrize_upper then writes the whole
- * y (fp32 and/or planes), mirroring every tile.  10 B of HBM traffic per matrix element instead of
- * 12, half the filter arithmetic.  Radius-4 blur only (int(4*sigma+0.5) == 4). */
+ * y (fp32 and/or planes; lo may be NULL when only the hi plane is wanted, i.e. for a single-MMA
+ * Diffuse), mirroring every tile.  10 B (8 B without lo) of HBM traffic per matrix element instead
+ * of 12, half the filter arithmetic.  Radius-4 blur only (int(4*sigma+0.5) == 4). */
 int sc_blur_upper_rowmax(sc_context* ctx, const float* a, int64_t n, int64_t lda,
                          const float* diag_override, double sigma, int zero_diagonal, float* b_out,
                          int64_t ldb, float* rowmax_out, void* stream);

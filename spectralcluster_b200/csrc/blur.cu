@@ -688,13 +688,15 @@ __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t 
     if (g.y) *reinterpret_cast<float4*>(g.y + i * g.ldy + j) = make_float4(y[0], y[1], y[2], y[3]);
     if (g.hi) {
       const __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
-      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-      const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y);
-      const __half2 l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
       *reinterpret_cast<uint2*>(g.hi + i * g.ldh + j) =
           make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(g.lo + i * g.ldh + j) =
-          make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      if (g.lo) {          // a single-MMA Diffuse reads only the hi plane
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(y[0] - f0.x, y[1] - f0.y);
+        const __half2 l1 = __floats2half2_rn(y[2] - f1.x, y[3] - f1.y);
+        *reinterpret_cast<uint2*>(g.lo + i * g.ldh + j) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
     }
   } else {
 #pragma unroll
@@ -705,7 +707,7 @@ __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t 
         __half h, l;
         split_half(y[t], h, l);
         g.hi[i * g.ldh + j + t] = h;
-        g.lo[i * g.ldh + j + t] = l;
+        if (g.lo) g.lo[i * g.ldh + j + t] = l;
       }
     }
   }
@@ -996,8 +998,8 @@ extern "C" int sc_threshold_symmetrize_upper(sc_context* ctx, const float* b, in
                                              float* y, int64_t ldy, void* hi, void* lo, int64_t ldh,
                                              void* stream) {
   SC_REQUIRE(ctx && b && rowmax && n > 0, "sc_threshold_symmetrize_upper: bad arguments");
-  SC_REQUIRE(y || (hi && lo), "sc_threshold_symmetrize_upper: no output given");
-  SC_REQUIRE((hi == nullptr) == (lo == nullptr), "hi/lo must come together");
+  SC_REQUIRE(y || hi, "sc_threshold_symmetrize_upper: no output given");
+  SC_REQUIRE(hi || !lo, "sc_threshold_symmetrize_upper: a lo plane needs its hi plane");
   SC_REQUIRE(sym_type == SC_SYMMETRIZE_MAX || sym_type == SC_SYMMETRIZE_AVERAGE,
              "Unsupported symmetrize_type.");
   SC_REQUIRE(vec_ok_f32(b, ldb) && aligned16(rowmax), "sc_threshold_symmetrize_upper: `b` / rowmax alignment");
@@ -1006,7 +1008,7 @@ extern "C" int sc_threshold_symmetrize_upper(sc_context* ctx, const float* b, in
   g.binarize = binarize; g.preserve_diag = preserve_diagonal; g.sym_type = sym_type;
   g.y = y; g.ldy = ldy; g.hi = (__half*)hi; g.lo = (__half*)lo; g.ldh = ldh;
   SC_REQUIRE(!y || vec_ok_f32(y, ldy), "sc_threshold_symmetrize_upper: `y` alignment");
-  SC_REQUIRE(!hi || (vec_ok_f16(hi, ldh) && vec_ok_f16(lo, ldh)), "sc_threshold_symmetrize_upper: plane alignment");
+  SC_REQUIRE(!hi || (vec_ok_f16(hi, ldh) && (!lo || vec_ok_f16(lo, ldh))), "sc_threshold_symmetrize_upper: plane alignment");
   g.tiles = (int)((n + UT - 1) / UT);
   const int64_t pairs = (int64_t)g.tiles * (g.tiles + 1) / 2;
   SC_REQUIRE(pairs < (1LL << 31), "sc_threshold_symmetrize_upper: n too large for the tile grid");

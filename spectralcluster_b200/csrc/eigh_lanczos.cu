@@ -66,19 +66,24 @@ k_symv_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds
 }
 
 // Y[p][row] = sum_col S[row][col] * T[p][col], p < P: tall-skinny product with the fp32 matrix read
-// once.  CTA = 8 warps x 4 rows; the T block is staged chunk by chunk in shared memory as
-// [p][col]; lanes walk consecutive columns (coalesced 128 B row segments, conflict-free fp64
-// shared reads); 4 x P fp64 accumulators per lane, reduced across the warp at the end.
+// once.  CTA = 8 warps x 4 rows.  Software pipeline over chunks of 256 columns: while chunk c is
+// multiplied, the 4 x 8 matrix elements per lane of chunk c+1 are already in flight into a
+// second register set and the T block of chunk c+1 lands in the other shared-memory buffer through
+// cp.async -- one barrier per chunk, no exposed HBM latency (the first version, load-then-use
+// with 1 CTA per SM, ran at 0.9 TB/s).  Lanes walk consecutive columns (coalesced 128 B row
+// segments, conflict-free fp64 shared reads); 4 x P fp64 accumulators per lane, reduced across
+// the warp at the end.
 constexpr int SYMM_ROWS_PER_WARP = 4;
 constexpr int SYMM_WARPS = 8;
-constexpr int SYMM_CHUNK = 256;    // columns of T staged per step: P * 256 * 8 B <= 32 KB
+constexpr int SYMM_CHUNK = 256;    // columns per pipeline step: 2 buffers x P x 256 x 8 B <= 64 KB
+constexpr int SYMM_ITERS = SYMM_CHUNK / 32;
 
 template <int P>
-__global__ void __launch_bounds__(SYMM_WARPS * 32)
+__global__ void __launch_bounds__(SYMM_WARPS * 32, 1)
 k_symm_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
-               const double* __restrict__ t /*[P][n]*/, double* __restrict__ y /*[P][ldy]*/,
-               int64_t ldy) {
-  __shared__ double ts[P][SYMM_CHUNK];
+               const double* __restrict__ t /*[P][ldt]*/, int64_t ldt,
+               double* __restrict__ y /*[P][ldy]*/, int64_t ldy) {
+  extern __shared__ double ts_raw[];                 // [2][P][SYMM_CHUNK]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * SYMM_WARPS + warp) * SYMM_ROWS_PER_WARP;
   const float* r[SYMM_ROWS_PER_WARP];
@@ -89,29 +94,69 @@ k_symm_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds
   for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[q][p] = 0.0;
-  for (int64_t c0 = 0; c0 < n; c0 += SYMM_CHUNK) {
-    const int64_t len = (n - c0 < SYMM_CHUNK) ? (n - c0) : SYMM_CHUNK;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < P * SYMM_CHUNK; idx += SYMM_WARPS * 32) {
-      const int p = idx / SYMM_CHUNK, j = idx - p * SYMM_CHUNK;
-      ts[p][j] = (j < len) ? t[(int64_t)p * n + c0 + j] : 0.0;
-    }
-    __syncthreads();
-    if (row0 < rows) {
-#pragma unroll 2
-      for (int j = lane; j < SYMM_CHUNK; j += 32) {
-        float q4[SYMM_ROWS_PER_WARP];
-#pragma unroll
-        for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
-          q4[q] = (j < len) ? ld_stream1(r[q] + c0 + j) : 0.0f;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const double tv = ts[p][j];                      // zero past len
-#pragma unroll
-          for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q) acc[q][p] = fma((double)q4[q], tv, acc[q][p]);
-        }
+  const int64_t chunks = (n + SYMM_CHUNK - 1) / SYMM_CHUNK;
+  // the T block is copied 16 bytes (2 doubles) at a time: ldt is even and t 16-byte aligned (the
+  // host pads); a last odd column goes through the scalar branch, columns past n read as zero
+  auto stage_t = [&](int64_t c, int buf) {
+    double* dst = ts_raw + (size_t)buf * P * SYMM_CHUNK;
+    const int64_t c0 = c * SYMM_CHUNK;
+    for (int idx = threadIdx.x; idx < P * (SYMM_CHUNK / 2); idx += SYMM_WARPS * 32) {
+      const int p = idx / (SYMM_CHUNK / 2), j2 = (idx - p * (SYMM_CHUNK / 2)) * 2;
+      double* d2 = dst + p * SYMM_CHUNK + j2;
+      if (c0 + j2 + 1 < n) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(d2)), "l"(t + (int64_t)p * ldt + c0 + j2)
+                     : "memory");
+      } else {
+        d2[0] = (c0 + j2 < n) ? t[(int64_t)p * ldt + c0 + j2] : 0.0;
+        d2[1] = 0.0;
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto load_s = [&](int64_t c, float (&q4)[SYMM_ITERS][SYMM_ROWS_PER_WARP]) {
+    const int64_t c0 = c * SYMM_CHUNK;
+#pragma unroll
+    for (int it = 0; it < SYMM_ITERS; ++it) {
+      const int64_t j = c0 + it * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
+        q4[it][q] = (j < n) ? ld_stream1(r[q] + j) : 0.0f;
+    }
+  };
+  auto multiply = [&](const float (&q4)[SYMM_ITERS][SYMM_ROWS_PER_WARP], int buf) {
+    const double* ts = ts_raw + (size_t)buf * P * SYMM_CHUNK;
+#pragma unroll
+    for (int it = 0; it < SYMM_ITERS; ++it) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const double tv = ts[p * SYMM_CHUNK + it * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q) acc[q][p] = fma((double)q4[it][q], tv, acc[q][p]);
+      }
+    }
+  };
+  float sa[SYMM_ITERS][SYMM_ROWS_PER_WARP], sb[SYMM_ITERS][SYMM_ROWS_PER_WARP];
+  stage_t(0, 0);
+  load_s(0, sa);
+  for (int64_t c = 0; c < chunks; c += 2) {
+    // ---- even chunk: registers `sa`, buffer 0; prefetch chunk c+1 into `sb`, buffer 1
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                       // buffer 0 landed; everybody has left buffer 1
+    if (c + 1 < chunks) {
+      stage_t(c + 1, 1);
+      load_s(c + 1, sb);
+    }
+    multiply(sa, 0);
+    if (c + 1 >= chunks) break;
+    // ---- odd chunk: registers `sb`, buffer 1; prefetch chunk c+2 into `sa`, buffer 0
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (c + 2 < chunks) {
+      stage_t(c + 2, 0);
+      load_s(c + 2, sa);
+    }
+    multiply(sb, 1);
   }
 #pragma unroll
   for (int q = 0; q < SYMM_ROWS_PER_WARP; ++q)
@@ -122,29 +167,40 @@ k_symm_f32_f64(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds
     }
 }
 
-static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t lds, const double* t,
-                       double* y, int64_t ldy, cudaStream_t st) {
+template <int P>
+static int launch_symm_p(const float* s, int64_t rows, int64_t n, int64_t lds, const double* t,
+                         int64_t ldt, double* y, int64_t ldy, cudaStream_t st) {
   const unsigned grid = (unsigned)((rows + SYMM_WARPS * SYMM_ROWS_PER_WARP - 1) /
                                    (SYMM_WARPS * SYMM_ROWS_PER_WARP));
-  switch (p) {
-    case 4: k_symm_f32_f64<4><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
-    case 8: k_symm_f32_f64<8><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
-    case 12: k_symm_f32_f64<12><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
-    case 16: k_symm_f32_f64<16><<<grid, SYMM_WARPS * 32, 0, st>>>(s, rows, n, lds, t, y, ldy); break;
-    default: set_error("sc_eigh_extremal: unsupported block size %d", p); return 2;
-  }
+  const size_t smem = sizeof(double) * 2 * P * SYMM_CHUNK;
+  auto kern = k_symm_f32_f64<P>;
+  SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, SYMM_WARPS * 32, smem, st>>>(s, rows, n, lds, t, ldt, y, ldy);
   sc::launched();
   return 0;
 }
 
+static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t lds, const double* t,
+                       int64_t ldt, double* y, int64_t ldy, cudaStream_t st) {
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(t) & 15) == 0 && ldt % 2 == 0 && ldt >= n,
+             "sc_eigh_extremal: internal (the block product wants an even ldt and an aligned T)");
+  switch (p) {
+    case 4: return launch_symm_p<4>(s, rows, n, lds, t, ldt, y, ldy, st);
+    case 8: return launch_symm_p<8>(s, rows, n, lds, t, ldt, y, ldy, st);
+    case 12: return launch_symm_p<12>(s, rows, n, lds, t, ldt, y, ldy, st);
+    case 16: return launch_symm_p<16>(s, rows, n, lds, t, ldt, y, ldy, st);
+    default: set_error("sc_eigh_extremal: unsupported block size %d", p); return 2;
+  }
+}
+
 // t_p = c .* x_p for the vectors p = blockIdx.y of a block (contiguous, stride n)
 __global__ void k_prescale(const double* __restrict__ x, const double* __restrict__ left,
-                           const double* __restrict__ right, int64_t n, double* __restrict__ t) {
+                           const double* __restrict__ right, int64_t n, double* __restrict__ t,
+                           int64_t ldt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t o = (int64_t)blockIdx.y * n + i;
   const double c = sqrt((left ? left[i] : 1.0) * (right ? right[i] : 1.0));
-  t[o] = c * x[o];
+  t[(int64_t)blockIdx.y * ldt + i] = c * x[(int64_t)blockIdx.y * n + i];
 }
 
 // w_p = flip * (delta .* x_p + sign * c .* y_p).  The products are stored in slabs of `slab_len`
@@ -505,8 +561,8 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
 
   for (;;) {
     // ---- one pass over S: W = flip * Op V[P..P+b)
-    k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb); sc::launched();
-    if (int rc = launch_symm(b, s, rows, n, lds, tb, y_mine, y_slab_len, st)) return rc;
+    k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb, ldt); sc::launched();
+    if (int rc = launch_symm(b, s, rows, n, lds, tb, ldt, y_mine, y_slab_len, st)) return rc;
     SC_LAUNCH_CHECK();
     if (gather) SC_REQUIRE(gather(user, b) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
     k_postscale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, y_base, y_slab_len, b, delta, left,

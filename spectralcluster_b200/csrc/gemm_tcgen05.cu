@@ -192,6 +192,47 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_m, int tiles
   return t;
 }
 
+// Incremental form of tile_coord for a CTA that walks tile, tile + stride, tile + 2 stride, ...:
+// the symmetric table search costs ~1.3 k instructions per call, which is noise at K = N but was a
+// third of the epilogue at K = d (affinity).  advance() moves the cursor forward inside the
+// (group, column block) enumeration instead of restarting it.
+template <bool SYM>
+struct TileCursor {
+  int tiles_m, tiles_n;
+  int g, nb, base;          // SYM: current group, column block, first tile index of (g, nb)
+  __device__ __forceinline__ void init(int tm, int tn) {
+    tiles_m = tm; tiles_n = tn; g = 0; nb = 0; base = 0;
+  }
+  __device__ __forceinline__ TileCoord at(int tile, const TileTable& tab) {
+    TileCoord t;
+    if (!SYM) {
+      const int group = GROUP_M * tiles_n;
+      const int gg = tile / group;
+      const int first_m = gg * GROUP_M;
+      const int gm = min(GROUP_M, tiles_m - first_m);
+      const int r = tile - gg * group;
+      t.m_blk = first_m + r % gm;
+      t.n_blk = r / gm;
+    } else {
+      // tiles are visited in increasing order: move forward only
+      while (g + 1 < tab.num_groups && tab.group_start[g + 1] <= tile) {
+        ++g;
+        nb = (g * GROUP_M) / 2;
+        base = tab.group_start[g];
+      }
+      for (;;) {
+        const int cnt = sym_valid_mblocks(g, nb, tiles_m);
+        if (tile - base < cnt) break;
+        base += cnt;
+        ++nb;
+      }
+      t.m_blk = g * GROUP_M + (tile - base);
+      t.n_blk = nb;
+    }
+    return t;
+  }
+};
+
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS_V2 = 128 + NUM_EPI_WARPS * 32;   // 384
 
@@ -289,13 +330,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
         // keep the live window (~70 MB) inside the 126 MB L2.
         const int ck_per_tile = (num_kb + pace_kb - 1) / pace_kb;
         unsigned int passed = 0;
+        TileCursor<SYM> cursor;
+        cursor.init(tiles_m, tiles_n);
         for (int round = 0; round * (int)gridDim.x < num_tiles; ++round) {
           const int tile = round * (int)gridDim.x + (int)blockIdx.x;
           if (tile >= num_tiles) {            // no tile in the last round: keep the targets reachable
             if (pace) atomicAdd(pace, (unsigned int)ck_per_tile);
             continue;
           }
-          const TileCoord tc = tile_coord<SYM>(tile, tiles_m, tiles_n, tab);
+          const TileCoord tc = cursor.at(tile, tab);
           const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
           for (int kb = 0; kb < num_kb; ++kb) {
             if (pace && kb % pace_kb == 0) {
@@ -383,8 +426,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
     const int half = (warp - 4) >> 2;                     // columns [128*half, +128)
     int acc = 0;
     uint32_t acc_phase = 0;
+    TileCursor<SYM> cursor;
+    cursor.init(tiles_m, tiles_n);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord<SYM>(tile, tiles_m, tiles_n, tab);
+      const TileCoord tc = cursor.at(tile, tab);
       float sum[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) sum[i] = 0.0f;
@@ -501,10 +546,19 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
             // and are skipped.
             float mx = 0.0f, sm = 0.0f;
             const int g = lane >> 2, w4 = lane & 3;
-            for (int r = 0; r < rows_valid; ++r) {
-              const float x = stg[r * 32 + ((g ^ (r & 7)) << 2) + w4];
-              mx = fmaxf(mx, x);
-              sm += x;
+            if (rows_valid == 32) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float x = stg[r * 32 + ((g ^ (r & 7)) << 2) + w4];
+                mx = fmaxf(mx, x);
+                if (EPI == TC_EPI_PLAIN) sm += x;
+              }
+            } else {
+              for (int r = 0; r < rows_valid; ++r) {
+                const float x = stg[r * 32 + ((g ^ (r & 7)) << 2) + w4];
+                mx = fmaxf(mx, x);
+                sm += x;
+              }
             }
             const int64_t tr = col0 + c * 32 + lane;
             if (tr < N) {

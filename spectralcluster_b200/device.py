@@ -21,9 +21,15 @@ from . import _native as nat
 
 _torch = None
 
-# MMAs per product of the Diffuse GEMM; the evidence for the default is in
-# profiles/r02_diffuse_precision.md (eigenvalue error, label equality per scheme).
-DEFAULT_DIFFUSE_PRECISION = "split3"
+# MMAs per product of the Diffuse GEMM inside predict().  "auto" picks by N from the measured error
+# of each scheme (profiles/r02_diffuse_precision.md): the rounding of the fp16 operand planes is a
+# zero-mean perturbation per product that averages down with sqrt(K) = sqrt(N).  In units of the
+# parity tolerance (|dw| <= 1e-5 |w| + 1e-6 max|w|) the worst eigenvalue error over configs[1],[2]
+# and seeds 0-4 was 0.85 (single) / 0.38 (split2) / 0.014 (split3) at N = 2,400 and 0.33 / 0.15 at
+# N = 16,384 -- labels identical in every run.  So: one MMA from N = 16,384 (<= 1/3 of the
+# tolerance, falling), two from N = 4,096, three below.
+DEFAULT_DIFFUSE_PRECISION = "auto"
+AUTO_SINGLE_FROM, AUTO_SPLIT2_FROM = 16384, 4096
 
 
 def torch():
@@ -64,7 +70,7 @@ class Engine:
     self.gemm_precision = nat.GEMM_SPLIT3       # affinity: its entries feed a threshold
     # Diffuse inside predict() (K = N): MMAs per product, SCB_DIFFUSE_PRECISION = split3 | split2
     # | single.  The operator-level API (refinement.Diffuse) always uses split3.
-    self.diffuse_precision = {"split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2,
+    self.diffuse_precision = {"auto": None, "split3": nat.GEMM_SPLIT3, "split2": nat.GEMM_SPLIT2,
                               "single": nat.GEMM_SINGLE}[
                                   os.environ.get("SCB_DIFFUSE_PRECISION", DEFAULT_DIFFUSE_PRECISION)]
     self.profile = None
@@ -78,6 +84,14 @@ class Engine:
       eng = cls(device)
       cls._instances[device] = eng
     return eng
+
+  def diffuse_precision_for(self, n: int) -> int:
+    """The sc_gemm_precision predict() uses for an n x n Diffuse (None = decide by n)."""
+    if self.diffuse_precision is not None:
+      return self.diffuse_precision
+    if n >= AUTO_SINGLE_FROM:
+      return nat.GEMM_SINGLE
+    return nat.GEMM_SPLIT2 if n >= AUTO_SPLIT2_FROM else nat.GEMM_SPLIT3
 
   # ---- buffers
   @property
@@ -219,9 +233,14 @@ class Engine:
     return b, m
 
   def threshold_symmetrize_upper(self, b, n, rowmax, p, mult, binarize, preserve_diag, sym_type,
-                                 want_f32, want_planes):
+                                 want_f32, want_planes, want_lo=True):
+    t = torch()
     y = self.matrix(n) if want_f32 else None
-    hi, lo = self.planes(n) if want_planes else (None, None)
+    hi = lo = None
+    if want_planes and want_lo:
+      hi, lo = self.planes(n)
+    elif want_planes:      # a single-MMA Diffuse reads only the hi plane: 2 B/element less to write
+      hi = t.empty((n, round_up(n, 64)), dtype=t.float16, device=self.device)
     self.call("sc_threshold_symmetrize_upper", _ptr(b), n, b.stride(0), _ptr(rowmax), float(p),
               float(mult), int(bool(binarize)), int(bool(preserve_diag)), int(sym_type), _ptr(y),
               0 if y is None else y.stride(0), _ptr(hi), _ptr(lo),
@@ -386,9 +405,12 @@ def run_refinement(eng: Engine, a, n: int, options, crop_vector=None, a_symmetri
       if eng.upper_pass_ok(sigma):
         # blur(A) is symmetric: blur the upper tiles once, keep them, mirror the result
         b, m = eng.blur_upper_rowmax(cur, n, sigma, diag, zero_diag)
+        want_lo = (diffuse_precision if diffuse_precision is not None
+                   else eng.gemm_precision) != nat.GEMM_SINGLE
         y, hi, lo = eng.threshold_symmetrize_upper(
             b, n, m, options.p_percentile, options.thresholding_soft_multiplier,
-            options.thresholding_with_binarization, zero_diag, sym_type, want_f32, want_planes)
+            options.thresholding_with_binarization, zero_diag, sym_type, want_f32, want_planes,
+            want_lo)
         del b
       else:
         m = eng.blur_rowmax(cur, n, sigma, diag, zero_diag)

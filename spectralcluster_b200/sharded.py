@@ -235,7 +235,7 @@ class ShardedRefiner:
     # it): a one-element all-reduce, stream-ordered, no host stall.
     be.stream_barrier(self.dist, self.group)
     self._mark("Y blocks visible")
-    n_planes = be.b_planes_needed()               # split2 / single read only the hi plane of B
+    n_planes = be.b_planes_needed(n)               # split2 / single read only the hi plane of B
     pulls = []
     for p, _, (c0, c1) in jobs:
       lo = plan.rows_of(p)[0]
@@ -389,7 +389,7 @@ class DeviceBackend:
     hi, lo = y_full
     ld = hi.stride(0)
     c = self.dev.ctypes.c_void_p
-    eng.call("sc_gemm_nt_planes", eng.diffuse_precision,
+    eng.call("sc_gemm_nt_planes", eng.diffuse_precision_for(n),
              c(hi.data_ptr() + 2 * a_row * ld), c(lo.data_ptr() + 2 * a_row * ld), ld, a_rows,
              c(hi.data_ptr() + 2 * b_row * ld), c(lo.data_ptr() + 2 * b_row * ld), ld, b_rows, n,
              c(s_block.data_ptr() + 4 * (s_row * s_block.stride(0) + b_row)), s_block.stride(0),
@@ -470,8 +470,8 @@ class DeviceBackend:
       self._flag = self.t.zeros((1,), dtype=self.t.float32, device=self.eng.device)
     dist.all_reduce(self._flag, group=group)
 
-  def b_planes_needed(self):
-    return 2 if self.eng.diffuse_precision == self.nat.GEMM_SPLIT3 else 1
+  def b_planes_needed(self, n):
+    return 2 if self.eng.diffuse_precision_for(n) == self.nat.GEMM_SPLIT3 else 1
 
   def pull_rows(self, local_planes, peer_addrs, row, rows):
     """Copy rows [row, row+rows) of the peer's planes into the same rows of the local planes on

@@ -93,7 +93,7 @@ class SpectralClusterer:
     refined = dev.run_refinement(eng, affinity.matrix, n, self.refinement_options,
                                  crop_vector=affinity.crop_vector,
                                  a_symmetric=affinity.symmetric,
-                                 diffuse_precision=eng.diffuse_precision)
+                                 diffuse_precision=eng.diffuse_precision_for(n))
     delta, left, right, sign, which = laplacian_lib.operator_terms(eng, refined,
                                                                    self.laplacian_type)
     descend = which == nat.EIG_LARGEST

@@ -3,7 +3,7 @@
   * Diffuse (refinement.py:232-234) at K = 16,384 and K = 65,536: 512 sampled rows of S = Y Y^T
     against the float64 product of the same fp32 Y (torch on the GPU, used as a checker only),
     rtol 3e-6 -- the two-level accumulation must hold its error at the headline K;
-  * configs[1] (ICASSP, no Laplacian) and configs[2] (GraphCut) at N = 8,192: the oracle's
+  * configs[1] (ICASSP, no Laplacian) and configs[2] (GraphCut) at N = 8,192 and 16,384: the oracle's
     refinement stage by stage in float64 on the host, LAPACK eigh of the symmetrised matrix
     (SURVEY.md A.2), eigengap and k-means -> eigenvalues within 1e-5 relative (+1e-6 lambda_max
     floor for the Laplacian's lambda_0 ~ 0) AND identical labels;
@@ -64,7 +64,7 @@ def test_diffuse_rows_vs_fp64_at_headline_k(engine, n):
   rel = (got - want).abs() / want.abs().clamp_min(1e-300)
   worst, rms = rel.max().item(), rel.pow(2).mean().sqrt().item()
   beyond = (rel > 3e-6).double().mean().item()
-  report("diffuse_fp64_rows_n%d" % n, dict(max_rel=worst, rms_rel=rms, frac_beyond_3e-6=beyond,
+  report("diffuse_fp64_rows_n%d" % n, dict(max_rel=worst, rms_rel=rms, frac_beyond_3e6=beyond,
                                            chains=n // 128))
   # fp32 round-to-nearest accumulation of n/128 chains: a random walk of ~3e-8 sqrt(n/128) per
   # element (6.8e-7 rms at n = 65,536); the maximum over 3.4e7 sampled elements sits near 5 sigma
@@ -105,9 +105,10 @@ def host_reference(x, laplacian, max_clusters, n_values):
   return w, k, orc.run_kmeans(v[:, :k], k)
 
 
-@pytest.mark.parametrize("laplacian,max_clusters,speakers", [(None, 7, 4), ("graphcut", 10, 6)])
-def test_configs_at_n8192_vs_float64_eigh(laplacian, max_clusters, speakers):
-  n = 8192
+@pytest.mark.parametrize("n,laplacian,max_clusters,speakers", [
+    (8192, None, 7, 4), (8192, "graphcut", 10, 6),
+    (16384, "graphcut", 10, 6)])       # 16,384: the size from which Diffuse issues a single MMA
+def test_configs_vs_float64_eigh(n, laplacian, max_clusters, speakers):
   x, truth = orc.synthetic_dvectors(n, 256, speakers, seed=0, return_labels=True)
   w_ref, k_ref, labels_ref = host_reference(x, laplacian, max_clusters, max_clusters + 1)
   c = scb.SpectralClusterer(
@@ -115,7 +116,7 @@ def test_configs_at_n8192_vs_float64_eigh(laplacian, max_clusters, speakers):
       laplacian_type=scb.LaplacianType.GraphCut if laplacian else None)
   labels = c.predict(x)
   w = c.last_details["eigenvalues"]
-  report("config_n8192_%s" % (laplacian or "nolaplacian"),
+  report("config_n%d_%s" % (n, laplacian or "nolaplacian"),
          dict(eigenvalues=w.tolist(), reference=w_ref.tolist(),
               tolerance_units=float(np.max(np.abs(w - w_ref) / (1e-5 * np.abs(w_ref) + 1e-6 * np.abs(w_ref).max()))),
               max_rel=float(np.max(np.abs(w - w_ref) / np.abs(w_ref).clip(1e-3 * np.abs(w_ref).max())))))

@@ -70,6 +70,8 @@ class FakeEngine:
   def symmetrize(self, a, n, kind): return self._rec("symmetrize", kind)
   def blur_rowmax(self, a, n, sigma, diag, zero_diag): return self._rec("blur_rowmax", sigma, diag)
 
+  gemm_precision = nat.GEMM_SPLIT3
+
   def upper_pass_ok(self, sigma):
     return dev.Engine.upper_pass_ok(sigma)
 
@@ -77,7 +79,8 @@ class FakeEngine:
     self._rec("blur_upper", sigma, diag)
     return "B", "m"
 
-  def threshold_symmetrize_upper(self, b, n, m, p, mult, binarize, keep, sym, want_f32, want_planes):
+  def threshold_symmetrize_upper(self, b, n, m, p, mult, binarize, keep, sym, want_f32, want_planes,
+                                 want_lo=True):
     self._rec("thrsym_upper", b, m, sym, want_f32, want_planes)
     return ("y" if want_f32 else None, "hi" if want_planes else None, "lo" if want_planes else None)
 
