@@ -229,14 +229,20 @@ int sc_memcpy_async(sc_context* ctx, void* dst, const void* src, int64_t bytes, 
  * w_host[0..n_values); unit-norm eigenvectors of M for the first n_vectors of them go to
  * v_dev, fp64 row-major [n, n_vectors].  SYNCHRONOUS (returns after the stream drains).
  *
- * sc_eigh_dense: Householder tridiagonalisation + implicit QL, all in fp64 on the device, full
- * spectrum (n_values <= n).  sc_eigh_extremal: thick-restart block Lanczos on the implicit operator
+ * sc_eigh_dense: Householder tridiagonalisation in fp64 on the device, then the full spectrum
+ * (n_values <= n <= 32768) by Sturm-count bisection (one thread per eigenvalue) with inverse
+ * iteration for the requested eigenvectors, or by implicit QL when (nearly) all eigenvectors are
+ * wanted at small n.  sc_eigh_extremal: thick-restart block Lanczos on the implicit operator
  * (fp32 S streamed from HBM once per block of vectors, fp64 vectors), n_values <= 32 << n.
  * stats_host[4] = {matrix-vector products, restarts, converged pairs, passes over S}. */
+/* sc_eigh_dense with pick != NULL: once the sorted eigenvalues are in w_host the callback decides
+ * how many eigenvectors are needed (the eigengap of utils.py:74-130 runs on the host) and hands
+ * back the device buffer [n, count] for them; n_vectors / v_dev are then ignored. */
+typedef int64_t (*sc_pick_fn)(void* user, const double* w_sorted, int64_t n_values, void** v_dev_out);
 int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t lds, const double* delta,
                   const double* left, const double* right, double sign, int which,
                   int64_t n_values, int64_t n_vectors, double* w_host, double* v_dev,
-                  void* stream);
+                  sc_pick_fn pick, void* user, void* stream);
 int sc_eigh_extremal(sc_context* ctx, const float* s, int64_t n, int64_t lds, const double* delta,
                      const double* left, const double* right, double sign, int which,
                      int64_t n_values, int64_t n_vectors, double tol, int64_t max_matvecs,

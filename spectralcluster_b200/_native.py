@@ -18,6 +18,8 @@ c_int = ctypes.c_int
 c_dbl = ctypes.c_double
 c_ptr = ctypes.c_void_p
 GATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int)   # sc_gather_fn
+PICK_FN = ctypes.CFUNCTYPE(ctypes.c_int64, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                           ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p))   # sc_pick_fn
 
 # name -> argtypes (every function returns int except the two noted); this table is also what
 # tests/test_abi.py checks against include/spectralcluster_b200.h.
@@ -70,7 +72,7 @@ PROTOTYPES = {
     "sc_ipc_close_all": [c_ptr],
     "sc_memcpy_async": [c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "sc_eigh_dense": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
-                      c_i64, c_ptr, c_ptr, c_ptr],
+                      c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "sc_eigh_extremal": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_dbl, c_int, c_i64,
                          c_i64, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "sc_eigh_block_size": [c_i64],

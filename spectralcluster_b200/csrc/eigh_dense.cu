@@ -18,7 +18,14 @@
 //   k_hh_symv         p <- T22 v          (warp per row, the HBM/L2-bound half of tridiag)
 //   k_hh_w            w <- tau p - (tau^2 p.v / 2) v
 //   k_hh_rank2        T22 <- T22 - v w^T - w v^T
-//   k_tql_rotations   implicit QL on (d, e); logs every Givens rotation  (one thread, O(n^2))
+//   k_sturm_bisect    every eigenvalue of (d, e) by Sturm-count bisection, one thread each: the
+//                     parallel route to the full spectrum (n > 256) -- O(n^2) work spread over n
+//                     threads instead of one thread's 3 n^2 dependent rotations
+//   k_invit_*         inverse iteration (pivoted LU of T - lambda I, one thread per requested
+//                     vector, workspaces interleaved for coalescing) + modified Gram-Schmidt
+//                     inside clusters of close eigenvalues, three rounds
+//   k_tql_rotations   implicit QL on (d, e), state in shared memory; logs every Givens rotation
+//                     (one thread, O(n^2)); used when many eigenvectors are wanted at small n
 //   k_apply_rotations Z <- Z G_1 G_2 ...  (one thread per row of Z, rotations streamed)
 //   k_backtransform   u <- H_0 ... H_{n-3} z, v <- E u / |E u|  (one CTA per eigenvector)
 #include "common.cuh"
@@ -148,10 +155,22 @@ struct QlStatus {
 // Implicit QL with Wilkinson shift (the classical tql2 recurrences, restated).  d: diagonal,
 // e[i]: coupling between i and i+1 (e[n-1] = 0).  One thread; the rotations are logged so that
 // the O(n^3) eigenvector update can run in parallel afterwards.
-__global__ void k_tql_rotations(double* __restrict__ d, double* __restrict__ e, int n,
+__global__ void k_tql_rotations(double* __restrict__ d_glob, double* __restrict__ e_glob, int n,
                                 double* __restrict__ rc, double* __restrict__ rs,
                                 long long rot_cap, Sweep* __restrict__ sweeps, int sweep_cap,
-                                QlStatus* __restrict__ out) {
+                                QlStatus* __restrict__ out, int use_smem) {
+  // the recurrence is one dependent chain: keep its state (2 n doubles) in shared memory when it
+  // fits -- every d[]/e[] access was a global round trip before (~1000 cycles per rotation)
+  extern __shared__ double ql_state[];
+  double* d = use_smem ? ql_state : d_glob;
+  double* e = use_smem ? ql_state + n : e_glob;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      d[i] = d_glob[i];
+      e[i] = e_glob[i];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double eps = 2.220446049250313e-16;
   long long nrot = 0;
@@ -208,6 +227,8 @@ __global__ void k_tql_rotations(double* __restrict__ d, double* __restrict__ e, 
   out->n_rot = nrot;
   out->n_sweeps = nsw;
   out->status = status;
+  if (use_smem)
+    for (int i = 0; i < n; ++i) d_glob[i] = d[i];
 }
 
 // zt is Z transposed: zt[col * n + row]; thread = row.  Z starts as the identity.
@@ -286,34 +307,225 @@ __global__ void k_backtransform(const double* __restrict__ t, int64_t n,
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v_out[i * n_sel + col] = u[i] * inv;
 }
 
+// ------------------------------------------------------------------ bisection + inverse iteration
+// Number of eigenvalues of the symmetric tridiagonal (d, e) that are < x (Sturm sequence of the
+// LDL^T pivots; tiny pivots are pushed to -pivmin as in LAPACK's dstebz).
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2,
+                                           int n, double x, double pivmin) {
+  double q = d[0] - x;
+  int cnt = (q < 0.0);
+  for (int k = 1; k < n; ++k) {
+    if (fabs(q) < pivmin) q = -pivmin;
+    q = d[k] - x - e2[k - 1] / q;
+    cnt += (q < 0.0);
+  }
+  return cnt;
+}
+
+// w[i] = i-th smallest eigenvalue, one thread per i, bisection on [lo, hi] (Gershgorin) until the
+// interval no longer shrinks in fp64.
+__global__ void k_sturm_bisect(const double* __restrict__ d, const double* __restrict__ e2, int n,
+                               double lo, double hi, double pivmin, double* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = lo, b = hi;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (a + b);
+    if (mid <= a || mid >= b) break;
+    if (sturm_count(d, e2, n, mid, pivmin) > i) b = mid;
+    else a = mid;
+  }
+  w[i] = 0.5 * (a + b);
+}
+
+__global__ void k_square(const double* __restrict__ e, int n, double* __restrict__ e2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) e2[i] = e[i] * e[i];
+}
+
+// Workspace of vector v, array `arr` (0..4: a, b, c, d2, pivot flag), entry k: interleaved over
+// the vectors so that the threads of a warp (one vector each) touch consecutive addresses.
+#define IW(arr, k) ws[((size_t)(arr) * n + (k)) * nvec + v]
+
+// Pivoted LU of T - lambda I (the dlagtf recurrences restated), one thread per vector.
+__global__ void k_invit_factor(const double* __restrict__ d, const double* __restrict__ e, int n,
+                               const double* __restrict__ lambda, int nvec,
+                               double* __restrict__ ws) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  const double lam = lambda[v];
+  for (int k = 0; k < n; ++k) {
+    IW(0, k) = d[k] - lam;
+    IW(1, k) = (k < n - 1) ? e[k] : 0.0;      // super-diagonal
+    IW(2, k) = (k < n - 1) ? e[k] : 0.0;      // sub-diagonal, becomes the multipliers
+    IW(3, k) = 0.0;                           // second super-diagonal created by pivoting
+    IW(4, k) = 0.0;                           // 1 = rows k, k+1 were interchanged
+  }
+  double scale1 = fabs(IW(0, 0)) + fabs(IW(1, 0));
+  for (int k = 0; k < n - 1; ++k) {
+    const double ak = IW(0, k), ck = IW(2, k);
+    double ak1 = IW(0, k + 1);
+    double scale2 = fabs(ck) + fabs(ak1);
+    if (k < n - 2) scale2 += fabs(IW(1, k + 1));
+    const double piv1 = (ak == 0.0) ? 0.0 : fabs(ak) / scale1;
+    if (ck == 0.0) {
+      scale1 = scale2;
+    } else {
+      const double piv2 = fabs(ck) / scale2;
+      if (piv2 <= piv1) {                      // no interchange
+        scale1 = scale2;
+        const double mult = ck / ak;
+        IW(2, k) = mult;
+        IW(0, k + 1) = ak1 - mult * IW(1, k);
+      } else {                                 // interchange rows k and k+1
+        const double mult = ak / ck;
+        IW(4, k) = 1.0;
+        IW(0, k) = ck;
+        const double bk = IW(1, k);
+        IW(0, k + 1) = bk - mult * ak1;
+        if (k < n - 2) {
+          const double bk1 = IW(1, k + 1);
+          IW(3, k) = bk1;
+          IW(1, k + 1) = -mult * bk1;
+        }
+        IW(1, k) = ak1;
+        IW(2, k) = mult;
+      }
+    }
+  }
+}
+
+// x <- (T - lambda I)^-1 x through the stored factors (dlagts, job -1 flavour: a vanishing pivot
+// is replaced by +-pivmin instead of overflowing); x is [nvec][n], contiguous per vector.
+__global__ void k_invit_solve(int n, int nvec, const double* __restrict__ ws, double pivmin,
+                              double* __restrict__ x) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  double* y = x + (size_t)v * n;
+  for (int k = 1; k < n; ++k) {
+    if (IW(4, k - 1) == 0.0) {
+      y[k] -= IW(2, k - 1) * y[k - 1];
+    } else {
+      const double temp = y[k - 1];
+      y[k - 1] = y[k];
+      y[k] = temp - IW(2, k - 1) * y[k];
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    double temp = y[k];
+    if (k < n - 1) temp -= IW(1, k) * y[k + 1];
+    if (k < n - 2) temp -= IW(3, k) * y[k + 2];
+    double ak = IW(0, k);
+    if (fabs(ak) < pivmin) ak = copysign(pivmin, ak == 0.0 ? 1.0 : ak);
+    y[k] = temp / ak;
+  }
+}
+#undef IW
+
+__global__ void k_invit_start(double* __restrict__ x, int n, int nvec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * nvec) return;
+  uint64_t z = 0x51ED270B0ull + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);   // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  x[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) + 0.25;
+}
+
+// One CTA per cluster of close eigenvalues [first, first+count): modified Gram-Schmidt in order,
+// every vector scaled to unit norm (singletons are just normalised).
+__global__ void k_invit_orthonormalize(double* __restrict__ x, int n,
+                                       const int* __restrict__ cluster_first,
+                                       const int* __restrict__ cluster_count) {
+  __shared__ double red[32];
+  const int first = cluster_first[blockIdx.x], count = cluster_count[blockIdx.x];
+  for (int a = 0; a < count; ++a) {
+    double* xa = x + (size_t)(first + a) * n;
+    for (int b = 0; b < a; ++b) {
+      const double* xb = x + (size_t)(first + b) * n;
+      double dot = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dot += xa[i] * xb[i];
+      dot = block_sum(dot, red);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) xa[i] -= dot * xb[i];
+      __syncthreads();
+    }
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ss += xa[i] * xa[i];
+    ss = block_sum(ss, red);
+    const double inv = 1.0 / sqrt(ss);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xa[i] *= inv;
+    __syncthreads();
+  }
+}
+
+// Global-memory twin of k_backtransform for n beyond the shared-memory budget: u is a per-vector
+// scratch row in HBM/L2.
+__global__ void k_backtransform_gmem(const double* __restrict__ t, int64_t n,
+                                     const double* __restrict__ tau, const double* __restrict__ zt,
+                                     const int* __restrict__ sel, int64_t n_sel,
+                                     const double* __restrict__ left, const double* __restrict__ right,
+                                     double* __restrict__ scratch, double* __restrict__ v_out) {
+  __shared__ double red[32];
+  const int64_t col = blockIdx.x;
+  const double* z = zt + (int64_t)sel[col] * n;
+  double* u = scratch + col * n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) u[i] = z[i];
+  __syncthreads();
+  for (int64_t j = n - 3; j >= 0; --j) {
+    const double tj = tau[j];
+    if (tj == 0.0) continue;
+    const int64_t m = n - j - 1;
+    const double* v = t + j * n + j + 1;
+    double dot = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) dot += v[i] * u[j + 1 + i];
+    dot = block_sum(dot, red);
+    const double f = tj * dot;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) u[j + 1 + i] -= f * v[i];
+    __syncthreads();
+  }
+  double ss = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ei = sqrt((left ? left[i] : 1.0) / (right ? right[i] : 1.0));
+    const double x = ei * u[i];
+    u[i] = x;
+    ss += x * x;
+  }
+  ss = block_sum(ss, red);
+  const double inv = 1.0 / sqrt(ss);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) v_out[i * n_sel + col] = u[i] * inv;
+}
+
 }  // namespace sc
 
 using namespace sc;
 
+typedef int64_t (*sc_pick_fn)(void* user, const double* w_sorted, int64_t n_values, void** v_dev_out);
+
 extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t lds,
                              const double* delta, const double* left, const double* right,
                              double sign, int which, int64_t n_values, int64_t n_vectors,
-                             double* w_host, double* v_dev, void* stream) {
+                             double* w_host, double* v_dev, sc_pick_fn pick, void* user,
+                             void* stream) {
   SC_REQUIRE(ctx && s && n > 0 && w_host, "sc_eigh_dense: bad arguments");
   SC_REQUIRE(n_values >= 0 && n_values <= n && n_vectors >= 0 && n_vectors <= n_values,
              "sc_eigh_dense: need 0 <= n_vectors <= n_values <= n");
-  SC_REQUIRE(n_vectors == 0 || v_dev, "sc_eigh_dense: v_dev missing");
-  SC_REQUIRE(n <= 16384, "sc_eigh_dense: n=%lld exceeds the dense solver limit (16384); use "
-             "sc_eigh_extremal", (long long)n);
+  SC_REQUIRE(pick || n_vectors == 0 || v_dev, "sc_eigh_dense: v_dev missing");
+  SC_REQUIRE(n <= 32768, "sc_eigh_dense: n=%lld exceeds the dense solver limit (32768: 8 n^2 B of "
+             "fp64 working matrix); use sc_eigh_extremal", (long long)n);
   cudaStream_t st = as_stream(stream);
   const size_t nn = (size_t)n * (size_t)n;
-  const long long rot_cap = 2LL * n * n + 1024;
-  const int sweep_cap = (int)std::min<long long>(64LL * n + 64, 2000000000LL);
 
   Scratch T, Zt, vec, rc, rs, sw, stat, selbuf;
   SC_CUDA(T.alloc(sizeof(double) * nn, st));
-  SC_CUDA(vec.alloc(sizeof(double) * (size_t)n * 6, st));
+  SC_CUDA(vec.alloc(sizeof(double) * (size_t)n * 8, st));
   double* d = vec.as<double>();
   double* e = d + n;
   double* tau = e + n;
   double* vbuf = tau + n;
   double* pbuf = vbuf + n;
   double* wbuf = pbuf + n;
+  double* e2 = wbuf + n;
+  double* wall = e2 + n;
 
   const unsigned gy = (unsigned)std::min<int64_t>((n + 255) / 256, 64);
   k_build_sym<<<dim3((unsigned)n, gy), 256, 0, st>>>(s, n, lds, delta, left, right, sign,
@@ -331,20 +543,58 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
   k_hh_tail<<<1, 32, 0, st>>>(T.as<double>(), n, d, e, tau); sc::launched();
   SC_LAUNCH_CHECK();
 
-  SC_CUDA(rc.alloc(sizeof(double) * (size_t)rot_cap, st));
-  SC_CUDA(rs.alloc(sizeof(double) * (size_t)rot_cap, st));
-  SC_CUDA(sw.alloc(sizeof(Sweep) * (size_t)sweep_cap, st));
-  SC_CUDA(stat.alloc(sizeof(QlStatus), st));
-  k_tql_rotations<<<1, 32, 0, st>>>(d, e, (int)n, rc.as<double>(), rs.as<double>(), rot_cap,
-                                    sw.as<Sweep>(), sweep_cap, stat.as<QlStatus>()); sc::launched();
-  SC_LAUNCH_CHECK();
-  QlStatus hs;
+  // Which route to the spectrum: implicit QL logs O(n^2) rotations from ONE thread and pays off only
+  // when (nearly) all eigenvectors are wanted at small n (the rotations rebuild Z for every row
+  // in parallel); everything else -- in particular the full-spectrum scan of max_clusters=None
+  // (utils.py:100-102) -- takes bisection + inverse iteration, which is parallel over eigenvalues.
+  const bool use_ql = (n <= 256) || (!pick && n_vectors > 64 && n <= 16384);
   std::vector<double> dh((size_t)n);
-  SC_CUDA(cudaMemcpyAsync(&hs, stat.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-  SC_CUDA(cudaMemcpyAsync(dh.data(), d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  SC_CUDA(cudaStreamSynchronize(st));
-  SC_REQUIRE(hs.status == 0, "sc_eigh_dense: implicit QL failed (status %d: 1=no convergence, "
-             "2=rotation log overflow, 3=sweep log overflow)", hs.status);
+  QlStatus hs = {};
+  if (use_ql) {
+    const long long rot_cap = 2LL * n * n + 1024;
+    const int sweep_cap = (int)std::min<long long>(64LL * n + 64, 2000000000LL);
+    SC_CUDA(rc.alloc(sizeof(double) * (size_t)rot_cap, st));
+    SC_CUDA(rs.alloc(sizeof(double) * (size_t)rot_cap, st));
+    SC_CUDA(sw.alloc(sizeof(Sweep) * (size_t)sweep_cap, st));
+    SC_CUDA(stat.alloc(sizeof(QlStatus), st));
+    const size_t ql_smem = sizeof(double) * 2 * (size_t)n;
+    const int in_smem = ql_smem <= ctx->smem_optin ? 1 : 0;
+    if (in_smem)
+      SC_CUDA(cudaFuncSetAttribute(k_tql_rotations, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)ql_smem));
+    k_tql_rotations<<<1, 256, in_smem ? ql_smem : 0, st>>>(d, e, (int)n, rc.as<double>(),
+                                                          rs.as<double>(), rot_cap, sw.as<Sweep>(),
+                                                          sweep_cap, stat.as<QlStatus>(), in_smem);
+    sc::launched();
+    SC_LAUNCH_CHECK();
+    SC_CUDA(cudaMemcpyAsync(&hs, stat.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaMemcpyAsync(dh.data(), d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    SC_REQUIRE(hs.status == 0, "sc_eigh_dense: implicit QL failed (status %d: 1=no convergence, "
+               "2=rotation log overflow, 3=sweep log overflow)", hs.status);
+  } else {
+    // Gershgorin interval and the pivot floor from (d, e) on the host (2 n doubles)
+    std::vector<double> eh((size_t)n);
+    SC_CUDA(cudaMemcpyAsync(dh.data(), d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaMemcpyAsync(eh.data(), e, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    double lo = dh[0], hi = dh[0], emax = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      const double r = (i > 0 ? std::fabs(eh[(size_t)i - 1]) : 0.0) + (i + 1 < n ? std::fabs(eh[(size_t)i]) : 0.0);
+      lo = std::min(lo, dh[(size_t)i] - r);
+      hi = std::max(hi, dh[(size_t)i] + r);
+      emax = std::max(emax, std::fabs(eh[(size_t)i]));
+    }
+    const double tnorm = std::max(std::fabs(lo), std::fabs(hi));
+    const double pivmin = std::max(2.2250738585072014e-308 * std::max(1.0, emax * emax), 1e-300);
+    const double margin = 2.0 * tnorm * 2.220446049250313e-16 * (double)n + 2.0 * pivmin;
+    k_square<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e, (int)n, e2); sc::launched();
+    k_sturm_bisect<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d, e2, (int)n, lo - margin, hi + margin,
+                                                            pivmin, wall); sc::launched();
+    SC_LAUNCH_CHECK();
+    SC_CUDA(cudaMemcpyAsync(dh.data(), wall, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+  }
 
   // host: order the spectrum (argsort of +-w, utils.py:62-67)
   std::vector<int> order((size_t)n);
@@ -355,7 +605,19 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dh[a] < dh[b]; });
   for (int64_t i = 0; i < n_values; ++i) w_host[i] = dh[(size_t)order[(size_t)i]];
 
-  if (n_vectors > 0) {
+  if (pick) {                      // the caller decides how many eigenvectors it needs from w
+    void* out = nullptr;
+    n_vectors = pick(user, w_host, n_values, &out);
+    SC_REQUIRE(n_vectors >= 0 && n_vectors <= n_values && (n_vectors == 0 || out),
+               "sc_eigh_dense: the pick callback returned a bad count / buffer");
+    v_dev = static_cast<double*>(out);
+  }
+  if (n_vectors == 0) return 0;
+
+  Scratch zsel, bt_scratch;
+  const double* zrows = nullptr;          // eigenvectors of the tridiagonal, one per row of length n
+  std::vector<int> sel((size_t)n_vectors);
+  if (use_ql) {
     SC_CUDA(Zt.alloc(sizeof(double) * nn, st));
     k_identity<<<(unsigned)n, 256, 0, st>>>(Zt.as<double>(), n); sc::launched();
     SC_LAUNCH_CHECK();
@@ -364,18 +626,71 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
           Zt.as<double>(), n, sw.as<Sweep>(), hs.n_sweeps, rc.as<double>(), rs.as<double>()); sc::launched();
       SC_LAUNCH_CHECK();
     }
-    SC_CUDA(selbuf.alloc(sizeof(int) * (size_t)n_vectors, st));
-    SC_CUDA(cudaMemcpyAsync(selbuf.p, order.data(), sizeof(int) * (size_t)n_vectors,
-                            cudaMemcpyHostToDevice, st));
-    const size_t smem = sizeof(double) * (size_t)n;
-    SC_REQUIRE(smem <= ctx->smem_optin, "sc_eigh_dense: n too large for back-transformation");
+    zrows = Zt.as<double>();
+    for (int64_t i = 0; i < n_vectors; ++i) sel[(size_t)i] = order[(size_t)i];
+  } else {
+    // inverse iteration for the first n_vectors eigenvalues of the requested order
+    const int nv = (int)n_vectors;
+    Scratch lam, ws, cf, cc;
+    SC_CUDA(lam.alloc(sizeof(double) * (size_t)nv, st));
+    SC_CUDA(ws.alloc(sizeof(double) * 5 * (size_t)n * (size_t)nv, st));
+    SC_CUDA(zsel.alloc(sizeof(double) * (size_t)n * (size_t)nv, st));
+    std::vector<double> lh((size_t)nv);
+    double tnorm = 0.0;
+    for (int64_t i = 0; i < n; ++i) tnorm = std::max(tnorm, std::fabs(dh[(size_t)i]));
+    tnorm = std::max(tnorm, 1e-300);
+    // clusters of close eigenvalues (dstein's 1e-3 |T| rule) are orthogonalised together; members
+    // are nudged apart by a few ulps so that their factorizations differ
+    std::vector<int> cfirst, ccount;
+    for (int i = 0; i < nv; ++i) {
+      lh[(size_t)i] = dh[(size_t)order[(size_t)i]];
+      const bool close = i > 0 && std::fabs(lh[(size_t)i] - dh[(size_t)order[(size_t)i - 1]]) <= 1e-3 * tnorm;
+      if (close) {
+        ++ccount.back();
+        const double sep = 10.0 * 2.220446049250313e-16 * tnorm;
+        const double dir = (which == SC_EIG_LARGEST) ? -1.0 : 1.0;
+        if (std::fabs(lh[(size_t)i] - lh[(size_t)i - 1]) < sep) lh[(size_t)i] = lh[(size_t)i - 1] + dir * sep;
+      } else {
+        cfirst.push_back(i);
+        ccount.push_back(1);
+      }
+    }
+    SC_CUDA(cf.alloc(sizeof(int) * cfirst.size(), st));
+    SC_CUDA(cc.alloc(sizeof(int) * ccount.size(), st));
+    SC_CUDA(cudaMemcpyAsync(lam.p, lh.data(), sizeof(double) * (size_t)nv, cudaMemcpyHostToDevice, st));
+    SC_CUDA(cudaMemcpyAsync(cf.p, cfirst.data(), sizeof(int) * cfirst.size(), cudaMemcpyHostToDevice, st));
+    SC_CUDA(cudaMemcpyAsync(cc.p, ccount.data(), sizeof(int) * ccount.size(), cudaMemcpyHostToDevice, st));
+    const double pivmin = 2.220446049250313e-16 * tnorm;
+    const unsigned gv = (unsigned)((nv + 31) / 32);
+    k_invit_factor<<<gv, 32, 0, st>>>(d, e, (int)n, lam.as<double>(), nv, ws.as<double>()); sc::launched();
+    k_invit_start<<<(unsigned)(((int64_t)n * nv + 255) / 256), 256, 0, st>>>(zsel.as<double>(), (int)n, nv); sc::launched();
+    for (int round = 0; round < 3; ++round) {
+      k_invit_solve<<<gv, 32, 0, st>>>((int)n, nv, ws.as<double>(), pivmin, zsel.as<double>()); sc::launched();
+      k_invit_orthonormalize<<<(unsigned)cfirst.size(), 256, 0, st>>>(zsel.as<double>(), (int)n,
+                                                                      cf.as<int>(), cc.as<int>()); sc::launched();
+    }
+    SC_LAUNCH_CHECK();
+    SC_CUDA(cudaStreamSynchronize(st));     // the host vectors above feed async copies
+    zrows = zsel.as<double>();
+    for (int64_t i = 0; i < n_vectors; ++i) sel[(size_t)i] = (int)i;
+  }
+  SC_CUDA(selbuf.alloc(sizeof(int) * (size_t)n_vectors, st));
+  SC_CUDA(cudaMemcpyAsync(selbuf.p, sel.data(), sizeof(int) * (size_t)n_vectors,
+                          cudaMemcpyHostToDevice, st));
+  const size_t smem = sizeof(double) * (size_t)n;
+  if (smem <= ctx->smem_optin) {
     SC_CUDA(cudaFuncSetAttribute(k_backtransform, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    k_backtransform<<<(unsigned)n_vectors, 256, smem, st>>>(T.as<double>(), n, tau,
-                                                            Zt.as<double>(), selbuf.as<int>(),
-                                                            n_vectors, left, right, v_dev); sc::launched();
-    SC_LAUNCH_CHECK();
-    SC_CUDA(cudaStreamSynchronize(st));   // `order` must outlive the H2D copy
+    k_backtransform<<<(unsigned)n_vectors, 256, smem, st>>>(T.as<double>(), n, tau, zrows,
+                                                            selbuf.as<int>(), n_vectors, left,
+                                                            right, v_dev); sc::launched();
+  } else {
+    SC_CUDA(bt_scratch.alloc(sizeof(double) * (size_t)n * (size_t)n_vectors, st));
+    k_backtransform_gmem<<<(unsigned)n_vectors, 512, 0, st>>>(T.as<double>(), n, tau, zrows,
+                                                              selbuf.as<int>(), n_vectors, left, right,
+                                                              bt_scratch.as<double>(), v_dev); sc::launched();
   }
+  SC_LAUNCH_CHECK();
+  SC_CUDA(cudaStreamSynchronize(st));   // `sel` must outlive the H2D copy
   return 0;
 }

@@ -306,13 +306,43 @@ class Engine:
     stats = np.zeros(4, dtype=np.int64)
     if dense:
       self.call("sc_eigh_dense", _ptr(s), n, s.stride(0), _ptr(delta), _ptr(left), _ptr(right),
-                float(sign), int(which), n_values, n_vectors, wp, _ptr(v), self.stream)
+                float(sign), int(which), n_values, n_vectors, wp, _ptr(v), None, None, self.stream)
     else:
       self.call("sc_eigh_extremal", _ptr(s), n, s.stride(0), _ptr(delta), _ptr(left),
                 _ptr(right), float(sign), int(which), n_values, n_vectors, float(tol),
                 int(max_matvecs), wp, _ptr(v), stats.ctypes.data_as(ctypes.c_void_p),
                 self.stream)
     return w[:n_values], v[:, :n_vectors], stats
+
+  def eigh_dense_pick(self, s, n, delta, left, right, sign, which, picker):
+    """Full spectrum by the dense solver; `picker(w) -> count` (host) decides from the sorted
+    eigenvalues how many eigenvectors are computed.  Returns (w[n], v device [n, count])."""
+    t = torch()
+    w = np.empty(n, dtype=np.float64)
+    box = {}
+
+    def pick(_user, w_ptr, n_values, out_ptr):
+      try:
+        count = int(picker(np.ctypeslib.as_array(w_ptr, shape=(int(n_values),)).copy()))
+        count = max(0, min(count, int(n_values)))
+        box["v"] = t.empty((n, max(count, 1)), dtype=t.float64, device=self.device)
+        out_ptr[0] = box["v"].data_ptr()
+        box["count"] = count
+        return count
+      except Exception as e:                         # never unwind through the C frame
+        box["error"] = e
+        return -1
+
+    callback = nat.PICK_FN(pick)
+    try:
+      self.call("sc_eigh_dense", _ptr(s), n, s.stride(0), _ptr(delta), _ptr(left), _ptr(right),
+                float(sign), int(which), n, 0, w.ctypes.data_as(ctypes.c_void_p), None, callback,
+                None, self.stream)
+    except nat.NativeError:
+      if "error" in box:
+        raise box["error"]
+      raise
+    return w, box["v"][:, :box["count"]]
 
   def row_renorm(self, e):
     self.call("sc_row_renorm", _ptr(e), int(e.shape[0]), int(e.shape[1]), self.stream)

@@ -121,11 +121,34 @@ class SpectralClusterer:
       self.last_details = dict(eigenvalues=np.array(w[:limit]), n_clusters_raw=k, max_gap=gap,
                                solver="krylov-schur", lanczos_stats=stats)
       return w, v, k, gap
-    # Lanczos needs a basis of m = max(2*limit+32, 64) vectors and n >= 4 m; it is ~600x faster
-    # than the full-spectrum Householder/QL solver at N = 2,048 (3 ms vs 2 s), so the dense solver
-    # is kept for small matrices and for max_clusters=None (every eigenvalue is needed).
+    # The block Lanczos solver needs n >= 4 max(2*limit+32, 64) and reads S a handful of times; the
+    # dense solver (Householder tridiagonalisation, 4/3 n^3) is kept for small matrices and for
+    # max_clusters=None / > 31 (every eigenvalue, or more than the extremal solver's 32, is needed).
     basis = max(2 * limit + 32, 64)
     dense = (n <= eng.dense_eig_max or n < 4 * basis or not self.max_clusters or limit > 32)
+
+    def count_clusters(values):
+      if descend:
+        return utils.compute_number_of_clusters(
+            values, max_clusters=self.max_clusters, stop_eigenvalue=self.stop_eigenvalue,
+            eigengap_type=self.eigengap_type, descend=True)
+      return utils.compute_number_of_clusters(
+          values, max_clusters=self.max_clusters, eigengap_type=self.eigengap_type, descend=False)
+
+    if dense and limit == n and n > 256:
+      # every eigenvalue is needed (max_clusters=None scans the whole spectrum, utils.py:100-102)
+      # but only the columns predict() will select: the eigengap runs between the two phases
+      picked = {}
+
+      def picker(values):
+        picked["k"], picked["gap"] = count_clusters(values)
+        return max(picked["k"], self.min_clusters or 0, 1)
+
+      w, v = eng.eigh_dense_pick(refined.s, n, delta, left, right, sign, which, picker)
+      k, gap = picked["k"], picked["gap"]
+      self.last_details = dict(eigenvalues=np.array(w[:limit]), n_clusters_raw=k, max_gap=gap,
+                               solver="dense", lanczos_stats=None)
+      return w, v, k, gap
     if dense:
       w, v, stats = eng.eigh(refined.s, n, delta, left, right, sign, which, n, n_vectors, True)
     else:

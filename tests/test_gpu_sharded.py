@@ -126,8 +126,8 @@ def test_parallel_autotune_two_ranks_matches_reference_fixture():
   assert out.get(timeout=30) == 1
 
 
-def _predict_worker(rank, world, port, use_nccl, out):
-  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _predict_worker(rank, world, port, use_nccl, transport, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SCB_SHARDED_TRANSPORT=transport)
   import torch
   import torch.distributed as dist
   torch.cuda.set_device(rank if use_nccl else 0)
@@ -151,6 +151,9 @@ def _predict_worker(rank, world, port, use_nccl, out):
                                scb.utils.enforce_ordered_labels(truth))
     w1, w2 = c.last_details["eigenvalues"], single.last_details["eigenvalues"]
     ok = ok and np.allclose(w1, w2[:len(w1)], rtol=1e-6, atol=1e-7 * np.abs(w2).max())
+    # two GPUs over NCCL: the NVLink peer-memory schedule unless send/recv was asked for
+    want = ("peer" if transport == "peer" else "nccl") if use_nccl else "gloo"
+    ok = ok and c.last_details["transport"] == want
   flags = torch.tensor([1 if ok else 0], device="cuda" if use_nccl else "cpu")
   dist.all_reduce(flags, op=dist.ReduceOp.MIN)
   if rank == 0:
@@ -158,15 +161,18 @@ def _predict_worker(rank, world, port, use_nccl, out):
   dist.destroy_process_group()
 
 
-def test_predict_sharded_two_ranks_matches_single_gpu():
+@pytest.mark.parametrize("transport", ["peer", "sendrecv"])
+def test_predict_sharded_two_ranks_matches_single_gpu(transport):
   import torch
   import torch.multiprocessing as mp
   use_nccl = torch.cuda.device_count() >= 2
+  if transport == "sendrecv" and not use_nccl:
+    pytest.skip("one GPU: the gloo run of the other parametrisation already is send/recv")
   s = socket.socket()
   s.bind(("127.0.0.1", 0))
   port = s.getsockname()[1]
   s.close()
   ctx = mp.get_context("spawn")
   out = ctx.Queue()
-  mp.spawn(_predict_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
+  mp.spawn(_predict_worker, args=(2, port, use_nccl, transport, out), nprocs=2, join=True)
   assert out.get(timeout=30) == 1

@@ -149,3 +149,39 @@ def test_parallel_autotune_two_ranks_gloo():
   out = ctx.Queue()
   mp.spawn(_autotune_worker, args=(2, free_port(), out), nprocs=2, join=True)
   assert out.get(timeout=10) == 1
+
+
+def _subgroup_worker(rank, world, port, n, out):
+  """Three processes, the refinement sharded over the sub-group {1, 2}: the plan speaks group-local
+  ranks, P2POp wants global ranks."""
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  group = dist.new_group([1, 2])
+  ok = True
+  if rank in (1, 2):
+    import spectralcluster_b200 as scb
+    from spectralcluster_b200 import sharded
+    from sharded_numpy_backend import NumpyBackend
+    from oracle import spectral_oracle as orc
+    RN = scb.RefinementName
+    opt = scb.RefinementOptions(gaussian_blur_sigma=1, p_percentile=0.9, refinement_sequence=[
+        RN.CropDiagonal, RN.GaussianBlur, RN.RowWiseThreshold, RN.Symmetrize, RN.Diffuse])
+    x = orc.synthetic_dvectors(n, 16, 3, seed=5)
+    res = sharded.ShardedRefiner(NumpyBackend(), opt, dist=dist, group=group).run(
+        x, 2, dist.get_rank(group))
+    plan = res["plan"]
+    want = orc.refine(orc.affinity(x), orc.options(
+        sequence=("crop", "blur", "threshold", "symmetrize", "diffuse"), sigma=1, p=0.9))
+    ok = np.allclose(res["s_block"], want[plan.row_begin:plan.row_end], rtol=1e-11, atol=1e-11)
+  flags = torch.tensor([1 if ok else 0])
+  dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+  if rank == 0:
+    out.put(int(flags[0]))
+  dist.destroy_process_group()
+
+
+def test_sharded_refinement_on_a_subgroup():
+  ctx = mp.get_context("spawn")
+  out = ctx.Queue()
+  mp.spawn(_subgroup_worker, args=(3, free_port(), 700, out), nprocs=3, join=True)
+  assert out.get(timeout=30) == 1
