@@ -209,6 +209,23 @@ int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_hi, const vo
                       int64_t n, int64_t k, float* c, int64_t ldc, float* c_mirror, int64_t ldm,
                       void* stream);
 
+/* ---- constraint operators (constraint.py:95-164) ---------------------------------------------- */
+/* Element-wise: mode 0 max(a, q) (AffinityIntegration Max, :112-113); 1 (a + q)/2 (Average,
+ * :114-115); 2 q > 0 ? 1 - (1 - q)(1 - a) : (1 + q) a (the propagation's final adjustment,
+ * :156-163, q = the propagated constraint matrix).  out may alias a. */
+int sc_constraint_combine(sc_context* ctx, const float* a, int64_t lda, const float* q, int64_t ldq,
+                          int64_t n, int mode, float* out, int64_t ldo, void* stream);
+/* out = alpha * diag(row_scale) x diag(col_scale) + beta * I (fp64 scale vectors, NULL = ones): the
+ * D^-1/2 A D^-1/2 normalisation (:145-147) and the I - alpha A / 2I - P steps of the Newton-Schulz
+ * inverse that replaces np.linalg.inv (:151).  out may alias x. */
+int sc_scale_shift(sc_context* ctx, const float* x, int64_t ldx, int64_t n, const double* row_scale,
+                   const double* col_scale, double alpha, double beta, float* out, int64_t ldo,
+                   void* stream);
+/* c[m,n] = a[m,k] b[n,k]^T, fp32 operands, fp64 accumulation (SIMT engine): the products of the
+ * propagation (:151-153) for matrices too small for a tcgen05 tile. */
+int sc_gemm_nt_f32(sc_context* ctx, const float* a, int64_t lda, const float* b, int64_t ldb,
+                   int64_t m, int64_t n, int64_t k, float* c, int64_t ldc, void* stream);
+
 /* ---- peer memory (one process per GPU, NVLink/NVSwitch) ------------------------------------ */
 /* CUDA IPC: export the allocation that contains dev_ptr (64-byte handle + byte offset of dev_ptr
  * inside it); open it in another process of the same box (peer access is enabled lazily); close

@@ -3,18 +3,19 @@ built from scratch for NVIDIA B200 (sm_100a).
 
 The package-level names mirror the reference's import surface for that path
 (/root/reference/spectralcluster/__init__.py:14-43): users switch by changing the import.
-Names of reference components outside the hot path (constraints, multi-stage / naive clusterers)
-are intentionally absent -- see DESIGN.md section 1.
+The multi-stage clusterer (a streaming wrapper around several clusterers) is the one reference
+component that is not mirrored -- see DESIGN.md section 1.
 """
 
-from . import (autotune, configs, custom_distance_kmeans, fallback_clusterer, laplacian,
-               naive_clusterer, refinement, spectral_clusterer, utils)
+from . import (autotune, configs, constraint, custom_distance_kmeans, fallback_clusterer,
+               laplacian, naive_clusterer, refinement, spectral_clusterer, utils)
 
 __version__ = "0.1.0"
 
 # public name -> defining submodule
 _EXPORTS = {
     autotune: ("AutoTune", "AutoTuneProxy"),
+    constraint: ("ConstraintOptions", "ConstraintName", "IntegrationType"),
     fallback_clusterer: ("FallbackOptions", "SingleClusterCondition", "FallbackClustererType"),
     laplacian: ("LaplacianType",),
     refinement: ("RefinementName", "RefinementOptions", "ThresholdType", "SymmetrizeType"),
@@ -27,6 +28,6 @@ for _module, _names in _EXPORTS.items():
     globals()[_name] = getattr(_module, _name)
 
 __all__ = sorted(n for names in _EXPORTS.values() for n in names) + [
-    "autotune", "configs", "custom_distance_kmeans", "fallback_clusterer", "laplacian",
+    "autotune", "configs", "constraint", "custom_distance_kmeans", "fallback_clusterer", "laplacian",
     "naive_clusterer", "refinement", "spectral_clusterer", "utils"]
 del _module, _names, _name

@@ -67,6 +67,9 @@ PROTOTYPES = {
     "sc_transpose": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_gemm_nt_planes": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64,
                           c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr],
+    "sc_constraint_combine": [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_i64, c_ptr],
+    "sc_scale_shift": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
+    "sc_gemm_nt_f32": [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "sc_ipc_export": [c_ptr, c_ptr, c_ptr, ctypes.POINTER(c_i64)],
     "sc_ipc_open": [c_ptr, c_ptr, c_i64, ctypes.POINTER(c_ptr)],
     "sc_ipc_close_all": [c_ptr],

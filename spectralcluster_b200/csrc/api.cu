@@ -162,3 +162,12 @@ extern "C" int sc_gemm_nt_planes(sc_context* ctx, int precision, const void* a_h
                          /*symmetric=*/true, /*diag_shift=*/0, nullptr, nullptr, c_mirror, ldm,
                          as_stream(stream));
 }
+
+// c[m,n] = a[m,k] b[n,k]^T with fp32 operands on the SIMT engine (fp64 accumulation): the small-
+// matrix twin of sc_gemm_nt_planes for the constraint propagation products (constraint.py:147-153).
+extern "C" int sc_gemm_nt_f32(sc_context* ctx, const float* a, int64_t lda, const float* b,
+                              int64_t ldb, int64_t m, int64_t n, int64_t k, float* c, int64_t ldc,
+                              void* stream) {
+  SC_REQUIRE(ctx && a && b && c && m > 0 && n > 0 && k > 0, "sc_gemm_nt_f32: bad arguments");
+  return gemm_nt_simt(0, a, lda, b, ldb, m, n, k, c, ldc, nullptr, as_stream(stream));
+}

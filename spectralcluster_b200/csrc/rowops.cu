@@ -293,6 +293,39 @@ __global__ void k_affinity_stats_finish(const double* __restrict__ part, const f
   }
 }
 
+// ------------------------------------------------------------------ constraint operators
+// constraint.py:95-164.  AffinityIntegration is one element-wise pass; ConstraintPropagation is a
+// handful of dense products (host-orchestrated, on the GEMM engines) around these element-wise
+// helpers.
+//   mode 0: out = max(a, q)                       AffinityIntegration(Max)      :112-113
+//   mode 1: out = (a + q) / 2                     AffinityIntegration(Average)  :114-115
+//   mode 2: out = q > 0 ? 1 - (1 - q)(1 - a) : (1 + q) a   propagation, eq. (4) :156-163
+__global__ void k_constraint_combine(const float* __restrict__ a, int64_t lda,
+                                     const float* __restrict__ q, int64_t ldq, int64_t n, int mode,
+                                     float* __restrict__ out, int64_t ldo) {
+  const int64_t i = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float x = a[i * lda + j], c = q[i * ldq + j];
+  float r;
+  if (mode == 0) r = fmaxf(x, c);
+  else if (mode == 1) r = 0.5f * (x + c);
+  else r = (c > 0.0f) ? 1.0f - (1.0f - c) * (1.0f - x) : (1.0f + c) * x;
+  out[i * ldo + j] = r;
+}
+
+// out = alpha * diag(r) x diag(c) + beta * I   (r, c fp64 vectors or NULL = ones)
+__global__ void k_scale_shift(const float* __restrict__ x, int64_t ldx, int64_t n,
+                              const double* __restrict__ r, const double* __restrict__ c,
+                              double alpha, double beta, float* __restrict__ out, int64_t ldo) {
+  const int64_t i = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double v = alpha * (double)x[i * ldx + j] * (r ? r[i] : 1.0) * (c ? c[j] : 1.0);
+  if (i == j) v += beta;
+  out[i * ldo + j] = (float)v;
+}
+
 // ------------------------------------------------------------------ row-wise normalise
 __global__ void k_row_normalize(const float* __restrict__ a, int64_t n, int64_t lda,
                                 float* __restrict__ out, int64_t ldo) {
@@ -465,6 +498,28 @@ extern "C" int sc_laplacian(sc_context* ctx, const float* w, int64_t n, int64_t 
   const unsigned gx = (unsigned)((n + 255) / 256);
   k_laplacian<<<dim3((unsigned)n, gx), 256, 0, st>>>(w, n, ldw, type, eps, deg.as<double>(), out,
                                                      ldo); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_constraint_combine(sc_context* ctx, const float* a, int64_t lda, const float* q,
+                                     int64_t ldq, int64_t n, int mode, float* out, int64_t ldo,
+                                     void* stream) {
+  SC_REQUIRE(ctx && a && q && out && n > 0 && mode >= 0 && mode <= 2, "sc_constraint_combine: bad arguments");
+  SC_REQUIRE(n <= 65535, "sc_constraint_combine: n too large for the element-wise grid");
+  k_constraint_combine<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, as_stream(stream)>>>(
+      a, lda, q, ldq, n, mode, out, ldo); sc::launched();
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sc_scale_shift(sc_context* ctx, const float* x, int64_t ldx, int64_t n,
+                              const double* row_scale, const double* col_scale, double alpha,
+                              double beta, float* out, int64_t ldo, void* stream) {
+  SC_REQUIRE(ctx && x && out && n > 0, "sc_scale_shift: bad arguments");
+  SC_REQUIRE(n <= 65535, "sc_scale_shift: n too large for the element-wise grid");
+  k_scale_shift<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, as_stream(stream)>>>(
+      x, ldx, n, row_scale, col_scale, alpha, beta, out, ldo); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

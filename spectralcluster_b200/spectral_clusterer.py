@@ -87,13 +87,32 @@ class SpectralClusterer:
     self.autotune_group = None
 
   # ------------------------------------------------------------------ eigen stage
-  def _eigen_on_device(self, eng, affinity: DeviceAffinity):
+  def _constrain(self, eng, affinity: "DeviceAffinity", constraint_matrix) -> "DeviceAffinity":
+    """constraint_operator.adjust_affinity on the resident affinity."""
+    q_host = np.asarray(constraint_matrix, dtype=np.float64)
+    op = self.constraint_options.constraint_operator
+    op.check_input(np.empty((affinity.n, affinity.n), dtype=np.bool_), q_host)
+    q = eng.upload_matrix(q_host)
+    out = op.adjust_on_device(eng, affinity.matrix, q, affinity.n)
+    sym = affinity.symmetric and bool(np.array_equal(q_host, q_host.T))
+    return DeviceAffinity(out, affinity.n, None, sym)
+
+  def _eigen_on_device(self, eng, affinity: DeviceAffinity, constraint_matrix=None):
     """Refinement + Laplacian terms + eigensolve; returns (w host, V device [n, nv], k, gap)."""
     n = affinity.n
     refined = dev.run_refinement(eng, affinity.matrix, n, self.refinement_options,
                                  crop_vector=affinity.crop_vector,
                                  a_symmetric=affinity.symmetric,
                                  diffuse_precision=eng.diffuse_precision_for(n))
+    if (self.constraint_options and not self.constraint_options.apply_before_refinement and
+        constraint_matrix is not None):
+      # constraint on the refined affinity (spectral_clusterer.py:137-142)
+      s = refined.s
+      if refined.row_scale is not None:
+        s = eng.row_normalize(s, n)
+      adjusted = self._constrain(eng, DeviceAffinity(s, n, None, refined.symmetric and
+                                                      refined.row_scale is None), constraint_matrix)
+      refined = dev.Refined(adjusted.matrix, n, adjusted.symmetric)
     delta, left, right, sign, which = laplacian_lib.operator_terms(eng, refined,
                                                                    self.laplacian_type)
     descend = which == nat.EIG_LARGEST
@@ -176,11 +195,9 @@ class SpectralClusterer:
     `affinity` is a host ndarray (reference signature) or a DeviceAffinity.  Eigenvectors come
     back as a host ndarray [n, n_vec] in the first case, a device fp64 tensor in the second;
     n_vec covers every column predict() can select (all n when max_clusters is None)."""
-    if constraint_matrix is not None and self.constraint_options:
-      raise NotImplementedError("constraints are outside the B200 hot path (SURVEY.md section 2)")
     eng = dev.Engine.get()
     if isinstance(affinity, DeviceAffinity):
-      _, v, k, gap = self._eigen_on_device(eng, affinity)
+      _, v, k, gap = self._eigen_on_device(eng, affinity, constraint_matrix)
       return v, k, gap
     a = np.asarray(affinity)
     if a.ndim != 2:
@@ -189,7 +206,7 @@ class SpectralClusterer:
       raise ValueError("affinity must be a square matrix")
     sym = bool(np.allclose(a, a.T, rtol=1e-6, atol=1e-9))
     da = DeviceAffinity(eng.upload_matrix(a), a.shape[0], None, sym)
-    _, v, k, gap = self._eigen_on_device(eng, da)
+    _, v, k, gap = self._eigen_on_device(eng, da, constraint_matrix)
     return v.to("cpu").numpy(), k, gap
 
   def _reduce_size_and_predict(self, embeddings: np.ndarray) -> np.ndarray:
@@ -222,9 +239,6 @@ class SpectralClusterer:
           (self.min_clusters and self.max_spectral_size <= self.min_clusters)):
         raise ValueError("max_spectral_size should be a relatively big number")
       return self._reduce_size_and_predict(embeddings)
-    if constraint_matrix is not None and self.constraint_options:
-      raise NotImplementedError("constraints are outside the B200 hot path")
-
     eng = dev.Engine.get()
     t = dev.torch()
     sequence = list(self.refinement_options.refinement_sequence or [])
@@ -246,6 +260,11 @@ class SpectralClusterer:
       if fallback_clusterer.check_single_cluster(self.fallback_options, embeddings, affinity):
         return np.array([0] * num_embeddings)
 
+    if (self.constraint_options and self.constraint_options.apply_before_refinement and
+        constraint_matrix is not None):
+      # constraint on the raw affinity (spectral_clusterer.py:258-264), on the device
+      affinity = self._constrain(eng, affinity, constraint_matrix)
+
     if self.autotune:
       if RefinementName.RowWiseThreshold not in sequence:
         raise ValueError("AutoTune is only effective when the refinement sequence"
@@ -254,7 +273,7 @@ class SpectralClusterer:
 
       def p_percentile_to_ratio(p_percentile: float):
         self.refinement_options.p_percentile = p_percentile   # shared state, as the reference
-        vectors, k, gap = self._compute_eigenvectors_ncluster(affinity)
+        vectors, k, gap = self._compute_eigenvectors_ncluster(affinity, constraint_matrix)
         if proxy == AutoTuneProxy.PercentileSqrtOverNME:
           return np.sqrt(1 - p_percentile) / gap, vectors, k
         if proxy == AutoTuneProxy.PercentileOverNME:
@@ -266,7 +285,7 @@ class SpectralClusterer:
       eigenvectors, n_clusters, best_p = self.autotune.tune(p_percentile_to_ratio)
       self.last_details["best_p_percentile"] = best_p
     else:
-      eigenvectors, n_clusters, _ = self._compute_eigenvectors_ncluster(affinity)
+      eigenvectors, n_clusters, _ = self._compute_eigenvectors_ncluster(affinity, constraint_matrix)
     del affinity
 
     return self._cluster_embeddings(eng, eigenvectors, n_clusters)

@@ -164,6 +164,50 @@ def nonsymmetric():
                           if k.endswith(("_k", "_p", "_gap"))})
 
 
+
+
+def constraints():
+  """constraint operators (constraint.py:95-164) and constrained predict()
+  (tests/spectral_clusterer_test.py:243-328, configs.turntodiarize_clusterer)."""
+  from spectralcluster import constraint as rc
+  rng = np.random.default_rng(21)
+  out = {}
+  x = orc.synthetic_dvectors(300, 32, 3, seed=2)
+  a = utils.compute_affinity_matrix(x)
+  scores = np.where(rng.random(300) < 0.1, rng.random(300) * 3 + 0.5, 0.0)
+  q = rc.ConstraintMatrix(list(scores), threshold=1).compute_diagonals()
+  out.update(a=a, q=q, scores=scores)
+  out["integ_max"] = rc.AffinityIntegration(rc.IntegrationType.Max).adjust_affinity(a, q)
+  out["integ_avg"] = rc.AffinityIntegration(rc.IntegrationType.Average).adjust_affinity(a, q)
+  for alpha in (0.4, 0.6):
+    out["prop_%d" % int(alpha * 10)] = rc.ConstraintPropagation(alpha).adjust_affinity(a, q)
+  # the non-symmetric 3x3 case of tests/constraint_test.py:25-32
+  a3 = np.array([[1, 0.25, 0], [0.31, 1, 0], [0, 0, 1]])
+  q3 = np.array([[1, 1, 0], [1, 1, 0], [0, 0, 0]])
+  out.update(a3=a3, q3=q3, prop3=rc.ConstraintPropagation(0.6).adjust_affinity(a3, q3))
+  # constrained predict(): Turn-to-Diarize preset on synthetic turns (fresh objects, quirk A.4-2)
+  from spectralcluster import configs as rcfg
+  c = ref.SpectralClusterer(
+      min_clusters=2, max_clusters=7,
+      refinement_options=ref.RefinementOptions(
+          thresholding_soft_multiplier=0.01, thresholding_type=ref.ThresholdType.Percentile,
+          thresholding_with_binarization=True, thresholding_preserve_diagonal=True,
+          symmetrize_type=ref.SymmetrizeType.Average,
+          refinement_sequence=[ref.RefinementName.RowWiseThreshold, ref.RefinementName.Symmetrize]),
+      constraint_options=rc.ConstraintOptions(
+          constraint_name=rc.ConstraintName.ConstraintPropagation, apply_before_refinement=True,
+          constraint_propagation_alpha=0.4),
+      autotune=ref.AutoTune(p_percentile_min=0.40, p_percentile_max=0.95, init_search_step=0.05,
+                            search_level=1),
+      laplacian_type=ref.LaplacianType.GraphCut, row_wise_renorm=True, custom_dist="cosine")
+  out["x"] = x
+  out["t2d_labels"] = c.predict(x, q)
+  out["t2d_p"] = np.array(c.refinement_options.p_percentile)
+  np.savez(os.path.join(OUT, "constraints.npz"), **out)
+  print("constraints: t2d clusters", len(set(out["t2d_labels"].tolist())), "p", out["t2d_p"])
+
+
 if __name__ == "__main__":
   main()
   nonsymmetric()
+  constraints()
