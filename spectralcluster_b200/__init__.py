@@ -3,12 +3,13 @@ built from scratch for NVIDIA B200 (sm_100a).
 
 The package-level names mirror the reference's import surface for that path
 (/root/reference/spectralcluster/__init__.py:14-43): users switch by changing the import.
-The multi-stage clusterer (a streaming wrapper around several clusterers) is the one reference
-component that is not mirrored -- see DESIGN.md section 1.
+Every module of the reference package has its mirror here; DESIGN.md section 1 says which parts
+run on the device and which are host logic around it.
 """
 
 from . import (autotune, configs, constraint, custom_distance_kmeans, fallback_clusterer,
-               laplacian, naive_clusterer, refinement, spectral_clusterer, utils)
+               laplacian, multi_stage_clusterer, naive_clusterer, refinement, spectral_clusterer,
+               utils)
 
 __version__ = "0.1.0"
 

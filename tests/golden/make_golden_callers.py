@@ -207,7 +207,31 @@ def constraints():
   print("constraints: t2d clusters", len(set(out["t2d_labels"].tolist())), "p", out["t2d_p"])
 
 
+def multistage():
+  """MultiStageClusterer.streaming_predict (multi_stage_clusterer.py:125-180)."""
+  from spectralcluster import multi_stage_clusterer as rm
+  x = orc.synthetic_dvectors(130, 24, 3, seed=9, turn=(8, 30))
+  out = {"x": x}
+  checkpoints = [5, 12, 30, 31, 45, 59, 60, 61, 90, 130]
+  for name in ("NoDeflicker", "OrderBased", "Hungarian"):
+    main = ref.SpectralClusterer(
+        min_clusters=1, max_clusters=5,
+        refinement_options=ref.RefinementOptions(
+            gaussian_blur_sigma=0, p_percentile=0.9,
+            refinement_sequence=ref.ICASSP2018_REFINEMENT_SEQUENCE))
+    ms = rm.MultiStageClusterer(main, fallback_threshold=0.5, L=8, U1=30, U2=60,
+                                deflicker=getattr(rm.Deflicker, name))
+    for i in range(130):
+      labels = ms.streaming_predict(x[i])
+      if i + 1 in checkpoints:
+        out["%s_%d" % (name, i + 1)] = np.asarray(labels)
+  out["checkpoints"] = np.array(checkpoints)
+  np.savez(os.path.join(OUT, "multistage.npz"), **out)
+  print("multistage:", {k: len(set(np.asarray(v).tolist())) for k, v in out.items() if k.endswith("_130")})
+
+
 if __name__ == "__main__":
   main()
   nonsymmetric()
   constraints()
+  multistage()

@@ -96,3 +96,21 @@ def test_max_spectral_size_argument_errors():     # spectral_clusterer.py:239-24
              dict(max_spectral_size=5, min_clusters=7)):
     with pytest.raises(ValueError):
       scb.SpectralClusterer(**kw).predict(x)
+
+
+def test_match_labels_known_answers():        # tests/multi_stage_clusterer_test.py:13-80
+  from spectralcluster_b200 import multi_stage_clusterer as ms
+  cases = [([1, 0], [0], [0, 1]),
+           ([0, 1, 2, 3, 4, 5], [0, 0, 0, 1, 2], [0, 3, 4, 1, 2, 5]),
+           ([0, 0, 0, 1, 1, 1, 2, 2], [0, 0, 1, 2, 2, 3, 4], [0, 0, 0, 2, 2, 2, 4, 4]),
+           ([1, 1, 1, 0, 0, 1], [0, 0, 0, 1, 1], [0, 0, 0, 1, 1, 0]),
+           ([1, 1, 1, 0, 0, 2], [0, 0, 0, 1, 1], [0, 0, 0, 1, 1, 2]),
+           ([0, 1, 1, 0, 0, 2], [0, 0, 0, 1, 1], [1, 0, 0, 1, 1, 2]),
+           ([0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5], [0, 0, 3, 3, 1, 1, 4, 4, 5, 5, 2],
+            [0, 0, 3, 3, 1, 1, 4, 4, 5, 5, 2, 2])]
+  for current, previous, want in cases:
+    np.testing.assert_array_equal(ms.match_labels(np.array(current), np.array(previous)), want)
+  with pytest.raises(ValueError):
+    ms.match_labels(np.array([0, 1]), np.array([0, 1]))
+  with pytest.raises(ValueError):
+    ms.MultiStageClusterer(scb.SpectralClusterer(max_spectral_size=50))
