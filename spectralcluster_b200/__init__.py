@@ -22,7 +22,8 @@ _EXPORTS = {
     refinement: ("RefinementName", "RefinementOptions", "ThresholdType", "SymmetrizeType"),
     spectral_clusterer: ("SpectralClusterer",),
     utils: ("EigenGapType",),
-    configs: ("ICASSP2018_REFINEMENT_SEQUENCE",),
+    configs: ("ICASSP2018_REFINEMENT_SEQUENCE", "TURNTODIARIZE_REFINEMENT_SEQUENCE"),
+    multi_stage_clusterer: ("Deflicker", "MultiStageClusterer"),
 }
 for _module, _names in _EXPORTS.items():
   for _name in _names:
@@ -30,5 +31,5 @@ for _module, _names in _EXPORTS.items():
 
 __all__ = sorted(n for names in _EXPORTS.values() for n in names) + [
     "autotune", "configs", "constraint", "custom_distance_kmeans", "fallback_clusterer", "laplacian",
-    "naive_clusterer", "refinement", "spectral_clusterer", "utils"]
+    "multi_stage_clusterer", "naive_clusterer", "refinement", "spectral_clusterer", "utils"]
 del _module, _names, _name
