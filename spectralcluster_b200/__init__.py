@@ -16,7 +16,8 @@ __version__ = "0.1.0"
 # public name -> defining submodule
 _EXPORTS = {
     autotune: ("AutoTune", "AutoTuneProxy"),
-    constraint: ("ConstraintOptions", "ConstraintName", "IntegrationType"),
+    constraint: ("ConstraintOptions", "ConstraintName", "ConstraintMatrix", "IntegrationType"),
+    naive_clusterer: ("NaiveClusterer",),
     fallback_clusterer: ("FallbackOptions", "SingleClusterCondition", "FallbackClustererType"),
     laplacian: ("LaplacianType",),
     refinement: ("RefinementName", "RefinementOptions", "ThresholdType", "SymmetrizeType"),
