@@ -465,12 +465,13 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   Scratch vb, vb2, work, small;
   SC_CUDA(vb.alloc(sizeof(double) * (size_t)jmax * n, st));
   SC_CUDA(vb2.alloc(sizeof(double) * (size_t)jmax * n, st));
-  SC_CUDA(work.alloc(sizeof(double) * (size_t)n * (3 * b), st));
+  const int64_t ldtb = (n + 1) & ~(int64_t)1;      // even: 16-byte aligned rows for cp.async
+  SC_CUDA(work.alloc(sizeof(double) * (size_t)(ldtb + 2 * n) * b, st));
   SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * jmax + 8 + jmax * 64), st));
   double* V = vb.as<double>();
   double* V2 = vb2.as<double>();
-  double* tb = work.as<double>();                  // [b][n] prescaled block
-  double* yb = tb + (size_t)b * n;                 // [b][n] products (unsharded)
+  double* tb = work.as<double>();                  // [b][ldtb] prescaled block
+  double* yb = tb + (size_t)b * ldtb;              // [b][n] products (unsharded)
   double* wb = yb + (size_t)b * n;                 // [b][n] Op applied, being orthogonalised
   double* h_dev = small.as<double>();              // [jmax]
   double* h2_dev = h_dev + jmax;                   // [jmax]
@@ -561,8 +562,8 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
 
   for (;;) {
     // ---- one pass over S: W = flip * Op V[P..P+b)
-    k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb, ldt); sc::launched();
-    if (int rc = launch_symm(b, s, rows, n, lds, tb, ldt, y_mine, y_slab_len, st)) return rc;
+    k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb, ldtb); sc::launched();
+    if (int rc = launch_symm(b, s, rows, n, lds, tb, ldtb, y_mine, y_slab_len, st)) return rc;
     SC_LAUNCH_CHECK();
     if (gather) SC_REQUIRE(gather(user, b) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
     k_postscale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, y_base, y_slab_len, b, delta, left,

@@ -49,7 +49,21 @@ __global__ void k_crop_diagonal(const float* a, int64_t n, int64_t lda, float* o
   const int64_t i = blockIdx.x;
   const float* r = a + i * lda;
   float m = 0.0f;  // the zeroed diagonal takes part in the max (refinement.py:148-149)
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x)
+  // 128-bit loads when the row is 16-byte aligned (every matrix the Python host allocates)
+  const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+  const int64_t n4 = vec ? (n & ~(int64_t)3) : 0;
+  for (int64_t j = (int64_t)threadIdx.x * 4; j < n4; j += (int64_t)blockDim.x * 4) {
+    const float4 q = *reinterpret_cast<const float4*>(r + j);
+    if (i < j || i > j + 3) {
+      m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+    } else {
+      if (j != i) m = fmaxf(m, q.x);
+      if (j + 1 != i) m = fmaxf(m, q.y);
+      if (j + 2 != i) m = fmaxf(m, q.z);
+      if (j + 3 != i) m = fmaxf(m, q.w);
+    }
+  }
+  for (int64_t j = n4 + threadIdx.x; j < n; j += blockDim.x)
     if (j != i) m = fmaxf(m, r[j]);
   m = block_max(m, red);
   if (diag_out && threadIdx.x == 0) diag_out[i] = m;
@@ -58,7 +72,19 @@ __global__ void k_crop_diagonal(const float* a, int64_t n, int64_t lda, float* o
     if (out == a) {
       if (threadIdx.x == 0) o[i] = m;
     } else {
-      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) o[j] = (j == i) ? m : r[j];
+      const bool ovec = vec && ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+      const int64_t o4 = ovec ? n4 : 0;
+      for (int64_t j = (int64_t)threadIdx.x * 4; j < o4; j += (int64_t)blockDim.x * 4) {
+        float4 q = *reinterpret_cast<const float4*>(r + j);
+        if (i >= j && i <= j + 3) {
+          if (j == i) q.x = m;
+          else if (j + 1 == i) q.y = m;
+          else if (j + 2 == i) q.z = m;
+          else q.w = m;
+        }
+        *reinterpret_cast<float4*>(o + j) = q;
+      }
+      for (int64_t j = o4 + threadIdx.x; j < n; j += blockDim.x) o[j] = (j == i) ? m : r[j];
     }
   }
 }
@@ -139,14 +165,22 @@ __global__ void k_row_threshold(const float* __restrict__ a, int64_t n, int64_t 
     const double d = (double)v1 - (double)v0;
     cut = (t >= 0.5) ? (double)v1 - d * (1.0 - t) : (double)v0 + d * t;   // numpy _lerp
   }
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-    const float v = (preserve_diag && j == i) ? 0.0f : r[j];
+  auto rule = [&](float x, int64_t j) -> float {
+    const float v = (preserve_diag && j == i) ? 0.0f : x;
     float y;
     if ((double)v < cut) y = v * mult;
     else y = binarize ? 1.0f : v;
     if (preserve_diag && j == i) y = 1.0f;
-    o[j] = y;
+    return y;
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(r) & 15) == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+  const int64_t n4 = vec ? (n & ~(int64_t)3) : 0;
+  for (int64_t j = (int64_t)threadIdx.x * 4; j < n4; j += (int64_t)blockDim.x * 4) {
+    const float4 q = *reinterpret_cast<const float4*>(r + j);
+    *reinterpret_cast<float4*>(o + j) =
+        make_float4(rule(q.x, j), rule(q.y, j + 1), rule(q.z, j + 2), rule(q.w, j + 3));
   }
+  for (int64_t j = n4 + threadIdx.x; j < n; j += blockDim.x) o[j] = rule(r[j], j);
 }
 
 // ------------------------------------------------------------------ symmetrize
@@ -333,10 +367,20 @@ __global__ void k_row_normalize(const float* __restrict__ a, int64_t n, int64_t 
   const int64_t i = blockIdx.x;
   const float* r = a + i * lda;
   float m = -INFINITY;
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, r[j]);
-  m = block_max(m, red);
   float* o = out + i * ldo;
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) o[j] = r[j] / m;   // refinement.py:244
+  const bool vec = ((reinterpret_cast<uintptr_t>(r) & 15) == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+  const int64_t n4 = vec ? (n & ~(int64_t)3) : 0;
+  for (int64_t j = (int64_t)threadIdx.x * 4; j < n4; j += (int64_t)blockDim.x * 4) {
+    const float4 q = *reinterpret_cast<const float4*>(r + j);
+    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+  for (int64_t j = n4 + threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, r[j]);
+  m = block_max(m, red);
+  for (int64_t j = (int64_t)threadIdx.x * 4; j < n4; j += (int64_t)blockDim.x * 4) {
+    const float4 q = *reinterpret_cast<const float4*>(r + j);
+    *reinterpret_cast<float4*>(o + j) = make_float4(q.x / m, q.y / m, q.z / m, q.w / m);   // refinement.py:244
+  }
+  for (int64_t j = n4 + threadIdx.x; j < n; j += blockDim.x) o[j] = r[j] / m;
 }
 
 // ------------------------------------------------------------------ Laplacian (materialised)

@@ -5,6 +5,7 @@ CUDA (csrc/kmeans.cu); only the MT19937 draws of RandomState(0) are taken on the
 
 from __future__ import annotations
 
+import dataclasses
 import typing
 
 import numpy as np
@@ -15,19 +16,81 @@ _METRICS = {"cosine": 0, "euclidean": 1}
 
 
 def run_kmeans(spectral_embeddings, n_clusters: int,
-               custom_dist: typing.Union[str, typing.Callable], max_iter: int) -> np.ndarray:
+               custom_dist: typing.Union[str, typing.Callable, None], max_iter: int) -> np.ndarray:
   """Cluster the rows of `spectral_embeddings` (host ndarray or device fp64 tensor) into
-  `n_clusters` groups; returns int64 labels on the host."""
-  if not isinstance(custom_dist, str) or custom_dist not in _METRICS:
-    raise NotImplementedError(
-        "custom_dist=%r: the B200 path implements 'cosine' and 'euclidean' "
-        "(arbitrary scipy metrics/callables are out of scope, SURVEY.md section 2 row 5)"
-        % (custom_dist,))
-  eng = dev.Engine.get()
-  t = dev.torch()
-  if isinstance(spectral_embeddings, np.ndarray):
-    e = t.from_numpy(np.ascontiguousarray(spectral_embeddings, dtype=np.float64)).to(eng.device)
-  else:
-    e = spectral_embeddings.contiguous()
-  labels, _ = eng.kmeans(e, int(n_clusters), _METRICS[custom_dist], int(max_iter))
-  return labels
+  `n_clusters` groups; returns int64 labels on the host.
+
+  "cosine" (every BASELINE configuration) and "euclidean" run entirely on the device.  The other
+  forms the reference accepts -- any scipy.spatial.distance metric name or callable
+  (custom_distance_kmeans.py:37-47; None fails in the reference, and here) -- are host code on the [n, k]
+  embeddings (k <= a few dozen columns; the N x N work is long done), exactly like the reference."""
+  if isinstance(custom_dist, str) and custom_dist in _METRICS:
+    eng = dev.Engine.get()
+    t = dev.torch()
+    if isinstance(spectral_embeddings, np.ndarray):
+      e = t.from_numpy(np.ascontiguousarray(spectral_embeddings, dtype=np.float64)).to(eng.device)
+    else:
+      e = spectral_embeddings.contiguous()
+    labels, _ = eng.kmeans(e, int(n_clusters), _METRICS[custom_dist], int(max_iter))
+    return labels
+  from sklearn.cluster import KMeans
+  e = (spectral_embeddings if isinstance(spectral_embeddings, np.ndarray)
+       else spectral_embeddings.to("cpu").numpy())
+  if not custom_dist:
+    # the reference builds this estimator and calls predict() without fitting it
+    # (custom_distance_kmeans.py:33-36,51): scikit-learn raises NotFittedError.  Same here.
+    return KMeans(n_clusters=n_clusters, init="k-means++", max_iter=300, random_state=0,
+                  n_init="auto").predict(e)
+  seed = KMeans(n_clusters=n_clusters, init="k-means++", max_iter=1, random_state=0,
+                n_init="auto").fit(e)
+  return CustomKMeans(n_clusters=n_clusters, centroids=seed.cluster_centers_, max_iter=max_iter,
+                      custom_dist=custom_dist).predict(e)
+
+
+@dataclasses.dataclass
+class CustomKMeans:
+  """Lloyd iterations under an arbitrary scipy distance (custom_distance_kmeans.py:55-141), host
+  arrays; `run_kmeans` uses the CUDA implementation of the same loop for cosine / euclidean."""
+  n_clusters: typing.Optional[int] = None
+  centroids: typing.Optional[np.ndarray] = None
+  max_iter: int = 10
+  tol: float = 0.001
+  custom_dist: typing.Union[str, typing.Callable] = "cosine"
+
+  def _init_centroids(self, embeddings: np.ndarray):
+    pick = np.random.choice(np.arange(embeddings.shape[0]), size=self.n_clusters, replace=False)
+    self.centroids = embeddings[pick, :]
+
+  def predict(self, embeddings: np.ndarray) -> np.ndarray:
+    from scipy.spatial import distance
+    n, d = embeddings.shape
+    if self.max_iter <= 0:
+      raise ValueError("Number of iterations should be a positive number,"
+                       " got %d instead" % self.max_iter)
+    if n < self.n_clusters:
+      raise ValueError("n_samples=%d should be >= n_clusters=%d" % (n, self.n_clusters))
+    if self.centroids is None:
+      self._init_centroids(embeddings)
+    if self.centroids.shape[0] != self.n_clusters:
+      raise ValueError("The shape of the initial centroids (%s)"
+                       "does not match the number of clusters %d"
+                       % (str(self.centroids.shape), self.n_clusters))
+    if self.centroids.shape[1] != d:
+      raise ValueError("The number of features of the initial centroids %d"
+                       "does not match the number of features of the data %d."
+                       % (self.centroids.shape[1], d))
+    rows = np.arange(n)
+    previous = 0
+    for step in range(self.max_iter + 1):
+      dist = distance.cdist(embeddings, self.centroids, metric=self.custom_dist)
+      labels = dist.argmin(axis=1)
+      mean = np.mean(dist[rows, labels])
+      settled = mean <= previous and mean >= (1 - self.tol) * previous
+      if settled or step == self.max_iter:
+        break
+      previous = mean
+      for c in range(self.n_clusters):
+        members = np.where(labels == c)[0]
+        if members.any():          # sic: a cluster holding only sample 0 keeps its centroid (A.4-3)
+          self.centroids[c] = np.mean(embeddings[members], axis=0)
+    return labels

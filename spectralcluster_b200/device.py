@@ -125,8 +125,39 @@ class Engine:
   def download_matrix(self, m, n: int) -> np.ndarray:
     return m[:, :n].to("cpu").numpy().astype(np.float64)
 
+  # C-ABI entry point -> the reference function whose work it does (NVTX range names)
+  REFERENCE_NAMES = {
+      "sc_normalize_rows": "utils.compute_affinity_matrix", "sc_affinity_cosine": "utils.compute_affinity_matrix",
+      "sc_crop_diagonal": "refinement.CropDiagonal", "sc_crop_diagonal_values": "refinement.CropDiagonal",
+      "sc_gaussian_blur": "refinement.GaussianBlur", "sc_gaussian_blur_rowmax": "refinement.GaussianBlur",
+      "sc_blur_upper_rowmax": "refinement.GaussianBlur",
+      "sc_blur_threshold_symmetrize": "refinement.RowWiseThreshold+Symmetrize",
+      "sc_threshold_symmetrize_upper": "refinement.RowWiseThreshold+Symmetrize",
+      "sc_row_threshold": "refinement.RowWiseThreshold", "sc_symmetrize": "refinement.Symmetrize",
+      "sc_diffuse": "refinement.Diffuse", "sc_gemm_nt_planes": "refinement.Diffuse",
+      "sc_row_normalize": "refinement.RowWiseNormalize", "sc_row_stats": "refinement.RowWiseNormalize",
+      "sc_laplacian": "laplacian.compute_laplacian",
+      "sc_eigh_dense": "utils.compute_sorted_eigenvectors",
+      "sc_eigh_extremal": "utils.compute_sorted_eigenvectors",
+      "sc_eigh_extremal_sharded": "utils.compute_sorted_eigenvectors",
+      "sc_kmeans": "custom_distance_kmeans.run_kmeans", "sc_row_renorm": "spectral_clusterer.row_wise_renorm",
+      "sc_affinity_stats": "fallback_clusterer.check_single_cluster",
+      "sc_constraint_combine": "constraint.adjust_affinity", "sc_scale_shift": "constraint.adjust_affinity",
+  }
+  nvtx = os.environ.get("SCB_NVTX") == "1"
+
   def call(self, name, *args, exc=nat.NativeError):
-    """One C-ABI call on the current stream; with `profile` on, bracketed by CUDA events."""
+    """One C-ABI call on the current stream; with `profile` on, bracketed by CUDA events; with
+    SCB_NVTX=1 inside an NVTX range named after the reference function it replaces."""
+    if self.nvtx:
+      torch().cuda.nvtx.range_push("%s [%s]" % (self.REFERENCE_NAMES.get(name, name), name))
+      try:
+        return self._call(name, *args, exc=exc)
+      finally:
+        torch().cuda.nvtx.range_pop()
+    return self._call(name, *args, exc=exc)
+
+  def _call(self, name, *args, exc=nat.NativeError):
     if self.profile is None:
       nat.call(name, self.ctx, *args, exc=exc)
       return

@@ -81,6 +81,10 @@ class SpectralClusterer:
     self.post_eigen_cluster_function = post_eigen_cluster_function
     # Diagnostics of the last predict(): eigenvalues used by the eigengap, cluster count, solver.
     self.last_details: typing.Dict[str, typing.Any] = {}
+    # Set collect_timings to get, after every predict(), last_timings = {C-ABI entry point: ms of
+    # device time (CUDA events)} -- the per-stage breakdown bench.py prints.
+    self.collect_timings = False
+    self.last_timings: typing.Dict[str, float] = {}
     # Set to a torch.distributed process group (or True for the default group) to spread the
     # AutoTune grid over the ranks, one p_percentile evaluation at a time per GPU
     # (BASELINE.json configs[4]); every rank must call predict() with the same embeddings.
@@ -223,6 +227,17 @@ class SpectralClusterer:
   # ------------------------------------------------------------------ predict
   def predict(self, embeddings: np.ndarray, constraint_matrix=None) -> np.ndarray:
     """Cluster the rows of `embeddings` ([n_samples, n_features] ndarray) -> int64 labels."""
+    if self.collect_timings and dev.torch().cuda.is_available():
+      eng = dev.Engine.get()
+      if eng.profile is None:
+        eng.start_profile()
+        try:
+          return self._predict(embeddings, constraint_matrix)
+        finally:
+          self.last_timings = eng.stop_profile()
+    return self._predict(embeddings, constraint_matrix)
+
+  def _predict(self, embeddings: np.ndarray, constraint_matrix=None) -> np.ndarray:
     num_embeddings = embeddings.shape[0]
     if not isinstance(embeddings, np.ndarray):
       raise TypeError("embeddings must be a numpy array")

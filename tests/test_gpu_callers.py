@@ -24,7 +24,7 @@ def load(name):
 
 def test_device_affinity_statistics_match_numpy(engine):
   z = load("single_cluster")
-  for a in (z["one"], z["many"]):
+  for row, a in enumerate((z["one"], z["many"])):
     n = a.shape[0]
     da = sc_mod.DeviceAffinity(engine.upload_matrix(a), n)
     got = fb.affinity_statistics(da)
@@ -34,7 +34,7 @@ def test_device_affinity_statistics_match_numpy(engine):
     for col, (name, thr) in enumerate(zip(z["conditions"], z["thresholds"])):
       opt = fb.FallbackOptions(single_cluster_condition=getattr(fb.SingleClusterCondition, str(name)),
                                single_cluster_affinity_threshold=float(thr))
-      want = bool(z["verdicts"][0 if a is z["one"] else 1, col])
+      want = bool(z["verdicts"][row, col])
       assert fb.check_single_cluster(opt, None, da) == want
 
 

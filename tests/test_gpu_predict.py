@@ -116,18 +116,21 @@ def test_compute_eigenvectors_ncluster_host_api():
     assert min(np.abs(v[:, col] - vr[:, col]).max(), np.abs(v[:, col] + vr[:, col]).max()) < 1e-5
 
 
-def test_unsupported_branches_raise():
+def test_option_errors_and_host_side_metrics():
   x = orc.synthetic_dvectors(300, 32, 3, seed=0)
-  with pytest.raises(NotImplementedError):
-    scb.SpectralClusterer(max_spectral_size=100, max_clusters=5).predict(x)
-  with pytest.raises(NotImplementedError):
-    scb.SpectralClusterer(min_clusters=1).predict(x)
-  with pytest.raises(NotImplementedError):       # threshold without symmetrize: non-symmetric
-    scb.SpectralClusterer(refinement_options=scb.RefinementOptions(
-        refinement_sequence=[RN.RowWiseThreshold])).predict(x)
-  with pytest.raises(ValueError):
+  with pytest.raises(ValueError):        # AutoTune without RowWiseThreshold (spectral_clusterer.py:268-272)
     scb.SpectralClusterer(autotune=scb.AutoTune(), refinement_options=scb.RefinementOptions(
         refinement_sequence=[RN.CropDiagonal])).predict(x)
+  # metrics beyond cosine / euclidean follow the reference on the host ([n, k] embeddings)
+  opt = orc.options(min_clusters=2, max_clusters=6, sequence=orc.ICASSP2018)
+  c = make_clusterer(opt)
+  c.custom_dist = "cityblock"
+  want = orc.predict(x, dict(opt, custom_dist="cityblock"))
+  assert np.array_equal(scb.utils.enforce_ordered_labels(c.predict(x)), orc.ordered(want))
+  import sklearn.exceptions
+  c.custom_dist = None                   # the reference never fits this estimator (:33-36,51)
+  with pytest.raises(sklearn.exceptions.NotFittedError):
+    c.predict(x)
 
 
 def test_user_hooks_still_work():
