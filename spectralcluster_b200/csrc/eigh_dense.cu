@@ -127,6 +127,171 @@ __global__ void k_hh_rank2(double* __restrict__ t, int64_t n, int64_t j,
   t[(j + 1 + r) * n + (j + 1 + c)] -= vr * wbuf[c] + wr * vbuf[c];
 }
 
+// ------------------------------------------------------------------ blocked tridiagonalisation
+// LAPACK's dsytrd/dlatrd scheme on the full (both triangles) fp64 matrix: inside a panel of NB
+// columns the trailing matrix is NOT touched -- column j is brought up to date from the panel's
+// (V, W) pairs, its reflector v_j is formed, p_j = A22 v_j streams the stale trailing matrix once
+// (the memory-bound half: n^3/3 elements in all) and is corrected with the same pairs; after the
+// panel A22 -= V W^T + W V^T is ONE rank-2NB update on the fp64 tensor cores (DMMA m8n8k4), which
+// replaces NB read-modify-write sweeps of the trailing matrix by one.
+constexpr int NB = 32;
+
+// Column j = j0 + k of the panel.  V, W are [NB][n] (vector-major).  One CTA.
+//   x[r]   = A[j][r] - sum_{i<k} (V_i[j] W_i[r] + W_i[j] V_i[r]),  r > j   (row j == column j)
+//   d[j]   = A[j][j] - 2 sum_{i<k} V_i[j] W_i[j]
+//   v (v[j+1] = 1), tau[j], e[j] = beta; v goes to row j of A (back-transformation), to V_k and vbuf
+__global__ void __launch_bounds__(1024)
+k_panel_column(double* __restrict__ a, int64_t n, int64_t j, int k, double* __restrict__ vv,
+               double* __restrict__ ww, double* __restrict__ d, double* __restrict__ e,
+               double* __restrict__ tau, double* __restrict__ vbuf) {
+  __shared__ double red[32];
+  __shared__ double sv[NB], sw[NB];
+  __shared__ double sh[2];
+  const int64_t m = n - j - 1;
+  if (threadIdx.x < k) {
+    sv[threadIdx.x] = vv[(int64_t)threadIdx.x * n + j];
+    sw[threadIdx.x] = ww[(int64_t)threadIdx.x * n + j];
+  }
+  __syncthreads();
+  double* x = a + j * n + j + 1;
+  double ss = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const int64_t r = j + 1 + i;
+    double val = x[i];
+    for (int q = 0; q < k; ++q) val -= sv[q] * ww[(int64_t)q * n + r] + sw[q] * vv[(int64_t)q * n + r];
+    x[i] = val;
+    if (i > 0) ss += val * val;
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) {
+    double dj = a[j * n + j];
+    for (int q = 0; q < k; ++q) dj -= 2.0 * sv[q] * sw[q];
+    d[j] = dj;
+    const double alpha = x[0];
+    if (ss == 0.0) {
+      tau[j] = 0.0;
+      e[j] = alpha;
+      sh[0] = 0.0;
+      sh[1] = 0.0;
+    } else {
+      const double beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+      tau[j] = (beta - alpha) / beta;
+      e[j] = beta;
+      sh[0] = 1.0 / (alpha - beta);
+      sh[1] = tau[j];
+    }
+  }
+  __syncthreads();
+  const double scale = sh[0];
+  const bool trivial = (sh[1] == 0.0);
+  double* vk = vv + (int64_t)k * n;
+  for (int64_t r = threadIdx.x; r <= j; r += blockDim.x) vk[r] = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const double v = (i == 0) ? 1.0 : (trivial ? 0.0 : x[i] * scale);
+    vbuf[i] = v;
+    x[i] = v;
+    vk[j + 1 + i] = v;
+  }
+}
+
+// p (from the stale trailing matrix) -> w_k.  One CTA of 32 warps: warp i takes the two dot
+// products with (V_i, W_i); then every thread corrects and scales its rows.
+__global__ void __launch_bounds__(1024)
+k_panel_w(int64_t n, int64_t j, int k, const double* __restrict__ tau, const double* __restrict__ vv,
+          double* __restrict__ ww, const double* __restrict__ vbuf, double* __restrict__ pbuf) {
+  __shared__ double red[32];
+  __shared__ double g1[NB], g2[NB];       // W_i^T v, V_i^T v
+  const int64_t m = n - j - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < k) {
+    const double* wi = ww + (int64_t)warp * n + j + 1;
+    const double* vi = vv + (int64_t)warp * n + j + 1;
+    double a1 = 0.0, a2 = 0.0;
+    for (int64_t i = lane; i < m; i += 32) {
+      const double v = vbuf[i];
+      a1 = fma(wi[i], v, a1);
+      a2 = fma(vi[i], v, a2);
+    }
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) { g1[warp] = a1; g2[warp] = a2; }
+  }
+  __syncthreads();
+  double pv = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const int64_t r = j + 1 + i;
+    double val = pbuf[i];
+    for (int q = 0; q < k; ++q) val -= vv[(int64_t)q * n + r] * g1[q] + ww[(int64_t)q * n + r] * g2[q];
+    pbuf[i] = val;
+    pv = fma(val, vbuf[i], pv);
+  }
+  pv = block_sum(pv, red);
+  const double tj = tau[j];
+  const double corr = 0.5 * tj * tj * pv;
+  double* wk = ww + (int64_t)k * n;
+  for (int64_t r = threadIdx.x; r <= j; r += blockDim.x) wk[r] = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) wk[j + 1 + i] = tj * pbuf[i] - corr * vbuf[i];
+}
+
+// A[r][c] -= sum_{i<kc} (V_i[r] W_i[c] + W_i[r] V_i[c]) for r, c >= lo: C -= P Q^T with
+// P = [V | W], Q = [W | V] (K = 2 kc), 64 x 64 tile per CTA, 8 warps x (8 rows x 64 columns), on the
+// fp64 tensor cores (mma.sync m8n8k4; SASS DMMA).
+constexpr int UPD_T = 64;
+constexpr int UPD_PITCH = 2 * NB + 4;     // doubles; == 4 mod 16: conflict-free 64-bit fragment loads
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+k_trailing_update(double* __restrict__ a, int64_t n, int64_t lo, int kc,
+                  const double* __restrict__ vv, const double* __restrict__ ww) {
+  extern __shared__ double upd_smem[];                       // P tile, Q tile: [64][UPD_PITCH] each
+  double* ps = upd_smem;
+  double* qs = upd_smem + UPD_T * UPD_PITCH;
+  const int64_t r0 = lo + (int64_t)blockIdx.y * UPD_T, c0 = lo + (int64_t)blockIdx.x * UPD_T;
+  const int kk = 2 * kc;
+  for (int idx = threadIdx.x; idx < kk * UPD_T; idx += blockDim.x) {
+    const int q = idx / UPD_T, t = idx - q * UPD_T;           // consecutive threads: consecutive rows
+    const double* pv = (q < kc) ? vv + (int64_t)q * n : ww + (int64_t)(q - kc) * n;
+    const double* qv = (q < kc) ? ww + (int64_t)q * n : vv + (int64_t)(q - kc) * n;
+    ps[t * UPD_PITCH + q] = (r0 + t < n) ? pv[r0 + t] : 0.0;
+    qs[t * UPD_PITCH + q] = (c0 + t < n) ? qv[c0 + t] : 0.0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fr = lane >> 2, fk = lane & 3;                    // fragment row (or column) / k index
+  double acc[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+  for (int k0 = 0; k0 < kk; k0 += 4) {
+    const double av = ps[(warp * 8 + fr) * UPD_PITCH + k0 + fk];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const double bv = qs[(t * 8 + fr) * UPD_PITCH + k0 + fk];
+      dmma_m8n8k4(acc[t][0], acc[t][1], av, bv);
+    }
+  }
+  const int64_t row = r0 + warp * 8 + fr;
+  if (row < n) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int64_t col = c0 + t * 8 + fk * 2;
+      double* dst = a + row * n + col;
+      if (col + 1 < n) {
+        double2 cur = *reinterpret_cast<double2*>(dst);
+        cur.x -= acc[t][0];
+        cur.y -= acc[t][1];
+        *reinterpret_cast<double2*>(dst) = cur;
+      } else if (col < n) {
+        dst[0] -= acc[t][0];
+      }
+    }
+  }
+}
+
 __global__ void k_hh_tail(const double* __restrict__ t, int64_t n, double* d, double* e,
                           double* tau) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -531,13 +696,39 @@ extern "C" int sc_eigh_dense(sc_context* ctx, const float* s, int64_t n, int64_t
   k_build_sym<<<dim3((unsigned)n, gy), 256, 0, st>>>(s, n, lds, delta, left, right, sign,
                                                     T.as<double>()); sc::launched();
   SC_LAUNCH_CHECK();
-  for (int64_t j = 0; j + 2 < n; ++j) {
-    const int64_t m = n - j - 1;
-    k_hh_reflector<<<1, 512, 0, st>>>(T.as<double>(), n, j, d, e, tau, vbuf); sc::launched();
-    k_hh_symv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(T.as<double>(), n, j, vbuf, pbuf); sc::launched();
-    k_hh_w<<<1, 512, 0, st>>>(tau, j, m, vbuf, pbuf, wbuf); sc::launched();
-    k_hh_rank2<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, st>>>(T.as<double>(), n,
-                                                                                j, vbuf, wbuf); sc::launched();
+  if (n < 256 || (n & 1)) {
+    // small (or odd-sized: the update uses 16-byte accesses) matrices: unblocked, rank-2 update per column
+    for (int64_t j = 0; j + 2 < n; ++j) {
+      const int64_t m = n - j - 1;
+      k_hh_reflector<<<1, 512, 0, st>>>(T.as<double>(), n, j, d, e, tau, vbuf); sc::launched();
+      k_hh_symv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(T.as<double>(), n, j, vbuf, pbuf); sc::launched();
+      k_hh_w<<<1, 512, 0, st>>>(tau, j, m, vbuf, pbuf, wbuf); sc::launched();
+      k_hh_rank2<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, st>>>(T.as<double>(), n,
+                                                                                  j, vbuf, wbuf); sc::launched();
+    }
+  } else {
+    Scratch panel;
+    SC_CUDA(panel.alloc(sizeof(double) * 2 * NB * (size_t)n, st));
+    double* vv = panel.as<double>();
+    double* ww = vv + (size_t)NB * n;
+    const size_t upd_smem = sizeof(double) * 2 * UPD_T * UPD_PITCH;
+    SC_CUDA(cudaFuncSetAttribute(k_trailing_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)upd_smem));
+    for (int64_t j0 = 0; j0 + 2 < n; j0 += NB) {
+      int kc = 0;
+      for (; kc < NB && j0 + kc + 2 < n; ++kc) {
+        const int64_t j = j0 + kc, m = n - j - 1;
+        k_panel_column<<<1, 1024, 0, st>>>(T.as<double>(), n, j, kc, vv, ww, d, e, tau, vbuf); sc::launched();
+        k_hh_symv<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(T.as<double>(), n, j, vbuf, pbuf); sc::launched();
+        k_panel_w<<<1, 1024, 0, st>>>(n, j, kc, tau, vv, ww, vbuf, pbuf); sc::launched();
+      }
+      const int64_t lo = j0 + kc;                 // first row / column of the trailing matrix
+      const unsigned tiles = (unsigned)((n - lo + UPD_T - 1) / UPD_T);
+      if (tiles > 0) {
+        k_trailing_update<<<dim3(tiles, tiles), 256, upd_smem, st>>>(T.as<double>(), n, lo, kc, vv, ww);
+        sc::launched();
+      }
+    }
   }
   SC_LAUNCH_CHECK();
   k_hh_tail<<<1, 32, 0, st>>>(T.as<double>(), n, d, e, tau); sc::launched();
