@@ -299,6 +299,59 @@ def mma_per_product(eng, n):
   return {nat.GEMM_SPLIT3: 3, nat.GEMM_SPLIT2: 2, nat.GEMM_SINGLE: 1}[eng.diffuse_precision_for(n)]
 
 
+def roofline_diffuse(eng, n, diffuse_ms, tensor_peak, peak_note, traffic):
+  """The dominant kernel against the measured tensor peak.  `achieved` counts the fp16 MMA flop the
+  kernel EXECUTES: it computes only the tiles that touch the upper triangle of S = Y Y^T and
+  mirrors them (N^3 multiply-adds x 2 / 2 per MMA plane), times the MMAs issued per product.
+  SURVEY.md 8(d) quotes 2 N^3 for the full product: reported beside it, not as the fraction."""
+  if not diffuse_ms:
+    return {"kernel": "k_gemm_tcgen05 (Diffuse, Y Y^T)", "bound": "tensor", "achieved": None,
+            "peak": tensor_peak, "unit": "TFLOP/s", "frac": None, "traffic": traffic}
+  mmas = mma_per_product(eng, n)
+  tri = 1.0 * n * n * n / (diffuse_ms * 1e-3) / 1e12          # N^3: the triangle, one MMA per product
+  return {"kernel": "k_gemm_tcgen05 (Diffuse, Y Y^T)", "bound": "tensor",
+          "achieved": tri * mmas, "peak": tensor_peak, "unit": "TFLOP/s",
+          "frac": tri * mmas / tensor_peak, "traffic": traffic, "peak_source": peak_note,
+          "basis": "executed fp16 MMA flop = %d x N^3 (upper-triangle tiles only, %d MMA(s) per "
+                   "product) / CUDA-event time of sc_diffuse" % (mmas, mmas),
+          "triangle_basis": {"achieved": tri, "frac": tri / tensor_peak,
+                             "note": "N^3 algorithmic flop of the triangle (SURVEY.md 8(d))"},
+          "full_product_basis": {"achieved": 2 * tri, "ratio_to_peak": 2 * tri / tensor_peak,
+                                 "note": "2 N^3 of the full product Y Y^T; the mirrored half is "
+                                         "stored, not computed, so this is a speed-up figure, "
+                                         "not a pipe utilisation"}}
+
+
+def roofline_refinement(eng, n, stages, steps, hbm_peak):
+  """Crop -> Blur -> RowMax threshold -> Symmetrize against the measured HBM bandwidth, on the
+  contract basis of SURVEY.md 8(d) (12 B per affinity element) and on the bytes the kernels
+  actually move."""
+  from spectralcluster_b200 import _native as nat
+  t1 = (stages.get("sc_blur_upper_rowmax", 0) + stages.get("sc_gaussian_blur_rowmax", 0)) / steps
+  t2 = (stages.get("sc_threshold_symmetrize_upper", 0) + stages.get("sc_blur_threshold_symmetrize", 0)) / steps
+  symmetric_pair = "sc_blur_upper_rowmax" in stages
+  if symmetric_pair:
+    # pass 1 reads the upper tiles of A and stores the upper tiles of B (2 + 2 B per matrix
+    # element); pass 2 reads them (2) and writes every element of Y: fp16 hi (+ lo) plane
+    y_bytes = 2 if eng.diffuse_precision_for(n) == nat.GEMM_SINGLE else 4
+    moved = 2 + 2 + 2 + y_bytes
+    how = "symmetric pair: blur the upper tiles once (read 2 + write 2 B/element), element-wise " \
+          "threshold/symmetrize with mirrored stores (read 2 + write %d B/element)" % y_bytes
+  else:
+    moved = 12
+    how = "two blur passes over the whole matrix (read 4, read 4 + write 4 B/element)"
+  tot = t1 + t2
+  gb = n * n / 1e9
+  return {"blur_rowmax_pass_ms": t1 or None, "threshold_symmetrize_pass_ms": t2 or None,
+          "fused_chain_GBps": 12 * gb / (tot / 1e3) if tot else None,
+          "fused_chain_frac": 12 * gb / (tot / 1e3) / hbm_peak if tot else None,
+          "basis": "12 B per affinity element (SURVEY.md 8(d)): read A, read A, write Y planes",
+          "moved_bytes_per_element": moved,
+          "moved_GBps": moved * gb / (tot / 1e3) if tot else None,
+          "moved_frac": moved * gb / (tot / 1e3) / hbm_peak if tot else None,
+          "kernels": how, "peak_GBps": hbm_peak}
+
+
 def load_peaks():
   try:
     return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -557,8 +610,6 @@ def main():
   peak_note = "measured (MEASURED_PEAKS.json, sustained fp16/bf16 dense)" if peaks else \
       "fallback (B200_PROFILING.md sustained)"
   diffuse_ms = stages.get("sc_diffuse", 0.0) / args.steps
-  flops = 2.0 * n * n * n           # algorithmic: full product Y Y^T
-  achieved = flops / (diffuse_ms * 1e-3) / 1e12 if diffuse_ms > 0 else None
   hbm_peak = peaks.get("hbm_gbs") or 6650.0
   # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same
   # workload (profiles/traffic.json: {"diffuse_n<N>": bytes per launch}); null when absent.
@@ -583,27 +634,8 @@ def main():
       "gpu_launches": int(launches),
       "eigensolve_ms": (stages.get("sc_eigh_extremal", 0.0) + stages.get("sc_eigh_dense", 0.0)) / args.steps,
       "stage_ms": {k: v / args.steps for k, v in sorted(stages.items())},
-      "roofline": {"kernel": "k_gemm_tcgen05 (Diffuse, Y Y^T)", "bound": "tensor",
-                   "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                   "frac": (achieved / tensor_peak) if achieved else None, "traffic": traffic,
-                   "peak_source": peak_note,
-                   "basis": "2 N^3 (full product, SURVEY.md 8(d))",
-                   "triangle_basis": {"achieved": achieved / 2 if achieved else None,
-                                      "frac": achieved / 2 / tensor_peak if achieved else None,
-                                      "note": "N^3: the kernel computes only the tiles that touch the "
-                                              "upper triangle and mirrors them"},
-                   "issued_mma": {"achieved": achieved / 2 * mma_per_product(eng, n) if achieved else None,
-                                  "frac": achieved / 2 * mma_per_product(eng, n) / tensor_peak if achieved else None,
-                                  "note": "fp16 MMA flop actually issued = %d x N^3" % mma_per_product(eng, n)},
-                   "note": "achieved = 2 N^3 algorithmic flop / CUDA-event time of sc_diffuse"},
-      "roofline_hbm_stages": (lambda t1, t2: {
-          "blur_stats_pass_GBps": (n * n * 4 / 1e9) / (t1 / 1e3) if t1 else None,
-          "blur_thrsym_pass_GBps": (n * n * 8 / 1e9) / (t2 / 1e3) if t2 else None,
-          "fused_chain_GBps": (n * n * 12 / 1e9) / ((t1 + t2) / 1e3) if (t1 and t2) else None,
-          "fused_chain_frac": (n * n * 12 / 1e9) / ((t1 + t2) / 1e3) / hbm_peak if (t1 and t2) else None,
-          "basis": "12 B per affinity element (SURVEY.md 8(d)): read A, read A, write Y planes",
-          "peak_GBps": hbm_peak})(stages.get("sc_gaussian_blur_rowmax", 0) / args.steps,
-                                  stages.get("sc_blur_threshold_symmetrize", 0) / args.steps),
+      "roofline": roofline_diffuse(eng, n, diffuse_ms, tensor_peak, peak_note, traffic),
+      "roofline_hbm_stages": roofline_refinement(eng, n, stages, args.steps, hbm_peak),
       "clocks": sampler.summary(),
   }
   if not args.no_cpu_baseline:

@@ -284,6 +284,157 @@ __global__ void k_combine(const double* __restrict__ v, int64_t n, int m,
     if (p0 + p < n_out) out[(int64_t)(p0 + p) * n + i] = acc[p];
 }
 
+// ---- block Gram-Schmidt: all b products of a pass are orthogonalised together, so the O(N m b)
+// vector work runs as a few grid-wide kernels per pass instead of 6 launches and one host
+// synchronisation per vector (at N = 65,536 the per-vector form cost more than the four passes
+// over S themselves: one CTA per basis vector streaming 2 x 512 KB).
+//
+// partial[c][j][p] = sum_{i in chunk c} V_j[i] W_p[i]   (j < cnt, p < B); fixed chunking and a
+// fixed-order second stage keep the result bit-reproducible (every rank of a sharded run must
+// take the same decisions).
+constexpr int BP_CHUNK = 256;      // rows per CTA
+constexpr int BP_WARPS = 8;
+
+template <int B>
+__global__ void __launch_bounds__(BP_WARPS * 32)
+k_block_proj(const double* __restrict__ v, int64_t n, int cnt, const double* __restrict__ w,
+             double* __restrict__ partial) {
+  __shared__ double ws[B][BP_CHUNK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * BP_CHUNK;
+  for (int idx = threadIdx.x; idx < B * BP_CHUNK; idx += BP_WARPS * 32) {
+    const int p = idx / BP_CHUNK, t = idx - p * BP_CHUNK;
+    ws[p][t] = (i0 + t < n) ? w[(int64_t)p * n + i0 + t] : 0.0;
+  }
+  __syncthreads();
+  for (int j = warp; j < cnt; j += BP_WARPS) {
+    const double* vj = v + (int64_t)j * n + i0;
+    double x[BP_CHUNK / 32];
+#pragma unroll
+    for (int t = 0; t < BP_CHUNK / 32; ++t) x[t] = (i0 + lane + 32 * t < n) ? vj[lane + 32 * t] : 0.0;
+    double acc[B];
+#pragma unroll
+    for (int p = 0; p < B; ++p) {
+      double a = 0.0;
+#pragma unroll
+      for (int t = 0; t < BP_CHUNK / 32; ++t) a = fma(x[t], ws[p][lane + 32 * t], a);
+      acc[p] = warp_sum(a);
+    }
+    if (lane == 0) {
+      double* out = partial + ((int64_t)blockIdx.x * cnt + j) * B;
+#pragma unroll
+      for (int p = 0; p < B; ++p) out[p] = acc[p];
+    }
+  }
+}
+
+// h[j*B + p] = sum_c partial[c][j][p], chunks in order
+__global__ void k_block_proj_reduce(const double* __restrict__ partial, int chunks, int total,
+                                    double* __restrict__ h) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * total + idx];
+  h[idx] = s;
+}
+
+// W_p -= sum_j h[j*B + p] V_j   (p < B)
+template <int B>
+__global__ void __launch_bounds__(256)
+k_block_axpy(const double* __restrict__ v, int64_t n, int cnt, const double* __restrict__ h,
+             double* __restrict__ w) {
+  extern __shared__ double hs[];                      // [cnt][B]
+  for (int idx = threadIdx.x; idx < cnt * B; idx += blockDim.x) hs[idx] = h[idx];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc[B];
+#pragma unroll
+  for (int p = 0; p < B; ++p) acc[p] = w[(int64_t)p * n + i];
+  for (int j = 0; j < cnt; ++j) {
+    const double x = v[(int64_t)j * n + i];
+#pragma unroll
+    for (int p = 0; p < B; ++p) acc[p] = fma(-hs[j * B + p], x, acc[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < B; ++p) w[(int64_t)p * n + i] = acc[p];
+}
+
+// b random vectors at once (vector p = blockIdx.y)
+__global__ void k_random_block(double* __restrict__ w, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(blockIdx.y + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  w[(int64_t)blockIdx.y * n + i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+template <int B>
+static int launch_block_proj(const double* v, int64_t n, int cnt, const double* w, double* partial,
+                             double* h, cudaStream_t st) {
+  const int chunks = (int)((n + BP_CHUNK - 1) / BP_CHUNK);
+  k_block_proj<B><<<chunks, BP_WARPS * 32, 0, st>>>(v, n, cnt, w, partial); sc::launched();
+  const int total = cnt * B;
+  k_block_proj_reduce<<<(total + 127) / 128, 128, 0, st>>>(partial, chunks, total, h); sc::launched();
+  return 0;
+}
+
+template <int B>
+static int launch_block_axpy(const double* v, int64_t n, int cnt, const double* h, double* w,
+                             cudaStream_t st) {
+  k_block_axpy<B><<<(unsigned)((n + 255) / 256), 256, sizeof(double) * cnt * B, st>>>(v, n, cnt, h, w);
+  sc::launched();
+  return 0;
+}
+
+#define SC_BLOCK_DISPATCH(b, CALL)                                     \
+  switch (b) {                                                         \
+    case 4: { constexpr int B_ = 4; CALL; } break;                     \
+    case 8: { constexpr int B_ = 8; CALL; } break;                     \
+    case 12: { constexpr int B_ = 12; CALL; } break;                   \
+    default: { constexpr int B_ = 16; CALL; } break;                   \
+  }
+
+// Upper-triangular Cholesky factor of the b x b Gram matrix g (row-major): g = R^T R.  Returns
+// false when a pivot falls below 1e-12 of the largest diagonal entry (a block that is rank
+// deficient to 1e-6: Cholesky-QR would lose orthogonality, the caller takes the vector-by-vector
+// path, which also knows how to continue past an exhausted invariant subspace).
+static bool cholesky_upper(const double* g, int b, std::vector<double>& r) {
+  r.assign((size_t)b * b, 0.0);
+  double dmax = 0.0;
+  for (int p = 0; p < b; ++p) dmax = std::max(dmax, g[(size_t)p * b + p]);
+  if (!(dmax > 0.0)) return false;
+  for (int p = 0; p < b; ++p) {
+    for (int q = 0; q <= p; ++q) {
+      double acc = g[(size_t)q * b + p];
+      for (int k = 0; k < q; ++k) acc -= r[(size_t)k * b + q] * r[(size_t)k * b + p];
+      if (q < p) {
+        r[(size_t)q * b + p] = acc / r[(size_t)q * b + q];
+      } else {
+        if (!(acc > 1e-12 * dmax)) return false;
+        r[(size_t)p * b + p] = std::sqrt(acc);
+      }
+    }
+  }
+  return true;
+}
+
+// inverse of an upper-triangular b x b matrix (row-major), into `inv` with leading dimension ld
+static void invert_upper(const std::vector<double>& r, int b, double* inv, int ld) {
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < b; ++j) inv[(size_t)i * ld + j] = 0.0;
+  for (int j = 0; j < b; ++j) {
+    inv[(size_t)j * ld + j] = 1.0 / r[(size_t)j * b + j];
+    for (int i = j - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int k = i + 1; k <= j; ++k) acc += r[(size_t)i * b + k] * inv[(size_t)k * ld + j];
+      inv[(size_t)i * ld + j] = -acc / r[(size_t)i * b + i];
+    }
+  }
+}
+
 // v_out[i, col] = E_i u_col[i] / |E u_col|  (row-major [n, n_out]); one CTA per column
 __global__ void k_mapback(const double* __restrict__ u, int64_t n, int n_out,
                           const double* __restrict__ left, const double* __restrict__ right,
@@ -467,7 +618,11 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   SC_CUDA(vb2.alloc(sizeof(double) * (size_t)jmax * n, st));
   const int64_t ldtb = (n + 1) & ~(int64_t)1;      // even: 16-byte aligned rows for cp.async
   SC_CUDA(work.alloc(sizeof(double) * (size_t)(ldtb + 2 * n) * b, st));
-  SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * jmax + 8 + jmax * 64), st));
+  SC_CUDA(small.alloc(sizeof(double) * (size_t)(2 * jmax + 8 + jmax * 64 + 2 * jmax * 16 + 256), st));
+  const int bp_chunks = (int)((n + BP_CHUNK - 1) / BP_CHUNK);
+  Scratch part;
+  SC_CUDA(part.alloc(sizeof(double) * (size_t)bp_chunks * jmax * 16, st));
+  double* partial = part.as<double>();
   double* V = vb.as<double>();
   double* V2 = vb2.as<double>();
   double* tb = work.as<double>();                  // [b][ldtb] prescaled block
@@ -477,6 +632,9 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   double* h2_dev = h_dev + jmax;                   // [jmax]
   double* nrm_dev = h2_dev + jmax;                 // [1] (+pad)
   double* z_dev = nrm_dev + 8;                     // [jmax x 64]
+  double* hb1_dev = z_dev + (size_t)jmax * 64;     // [jmax x b] block Gram-Schmidt coefficients
+  double* hb2_dev = hb1_dev + (size_t)jmax * 16;   // [jmax x b] second sweep
+  double* g_dev = hb2_dev + (size_t)jmax * 16;     // [b x b] Gram matrix of the block
   // where the block product lands and how postscale finds element i of vector p
   double* y_base = y_ext ? y_ext : yb;
   const int64_t y_slab_len = y_ext ? slab_len : n;
@@ -517,9 +675,52 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
     return 0;
   };
 
+  // ---- block forms (see k_block_proj): Gram matrix of a block, Cholesky-QR twice
+  std::vector<double> hb1((size_t)jmax * 16), hb2((size_t)jmax * 16), gram((size_t)16 * 16);
+  std::vector<double> zk1((size_t)16 * 64), zk2((size_t)16 * 64), R1, R2, Rtot((size_t)16 * 16);
+  auto gram_of = [&](const double* w) -> int {       // gram <- W^T W (host), one synchronisation
+    SC_BLOCK_DISPATCH(b, if (int rc = launch_block_proj<B_>(w, n, b, w, partial, g_dev, st)) return rc);
+    SC_LAUNCH_CHECK();
+    SC_CUDA(cudaMemcpyAsync(gram.data(), g_dev, sizeof(double) * b * b, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  // q_out <- orthonormal basis of span(W) by Cholesky-QR applied twice, W = Q Rtot; `gram` already
+  // holds W^T W.  Returns 0, or -1 when the block is (numerically) rank deficient -- W untouched.
+  // tmp: b x n scratch, distinct from w and q_out.
+  auto cholqr2 = [&](const double* w, double* tmp, double* q_out, int* status) -> int {
+    *status = -1;
+    if (!cholesky_upper(gram.data(), b, R1)) return 0;
+    invert_upper(R1, b, zk1.data(), 64);
+    SC_CUDA(cudaMemcpyAsync(z_dev, zk1.data(), sizeof(double) * (size_t)b * 64, cudaMemcpyHostToDevice, st));
+    k_combine<<<dim3(gn, (unsigned)((b + 7) / 8)), 256, 0, st>>>(w, n, b, z_dev, 64, b, tmp); sc::launched();
+    if (int rc = gram_of(tmp)) return rc;
+    if (!cholesky_upper(gram.data(), b, R2)) return 0;
+    invert_upper(R2, b, zk2.data(), 64);
+    SC_CUDA(cudaMemcpyAsync(z_dev + 16 * 64, zk2.data(), sizeof(double) * (size_t)b * 64,
+                            cudaMemcpyHostToDevice, st));
+    k_combine<<<dim3(gn, (unsigned)((b + 7) / 8)), 256, 0, st>>>(tmp, n, b, z_dev + 16 * 64, 64, b, q_out); sc::launched();
+    SC_LAUNCH_CHECK();
+    for (int i = 0; i < b; ++i)
+      for (int j = 0; j < b; ++j) {
+        double acc = 0.0;
+        for (int k = i; k <= j; ++k) acc += R2[(size_t)i * b + k] * R1[(size_t)k * b + j];
+        Rtot[(size_t)i * b + j] = (j >= i) ? acc : 0.0;
+      }
+    *status = 0;
+    return 0;
+  };
+
   // start block: b random orthonormal vectors
-  for (int p = 0; p < b; ++p)
-    if (int rc = random_direction(p)) return rc;
+  {
+    k_random_block<<<dim3(gn, b), 256, 0, st>>>(wb, n, 0x5CB200ull + 7919ull * reseed++); sc::launched();
+    int status = -1;
+    if (int rc = gram_of(wb)) return rc;
+    if (int rc = cholqr2(wb, tb, V, &status)) return rc;
+    if (status != 0)
+      for (int p = 0; p < b; ++p)
+        if (int rc = random_direction(p)) return rc;
+  }
 
   int P = 0, J = b;
   int64_t matvecs = 0, restarts = 0, passes = 0;
@@ -570,15 +771,43 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
                                              right, sign, flip, n, wb); sc::launched();
     matvecs += b;
     ++passes;
-    // ---- orthogonalise the b products one at a time; each yields one new basis vector
-    for (int p = 0; p < b; ++p) {
+    // ---- block classical Gram-Schmidt (twice) of all b products against the basis, then
+    // Cholesky-QR (twice) inside the block: T[0:J, P:P+b] = V^T W, T[J:J+b, P:P+b] = R
+    SC_BLOCK_DISPATCH(b, {
+      if (int rc = launch_block_proj<B_>(V, n, J, wb, partial, hb1_dev, st)) return rc;
+      if (int rc = launch_block_axpy<B_>(V, n, J, hb1_dev, wb, st)) return rc;
+      if (int rc = launch_block_proj<B_>(V, n, J, wb, partial, hb2_dev, st)) return rc;
+      if (int rc = launch_block_axpy<B_>(V, n, J, hb2_dev, wb, st)) return rc;
+    });
+    SC_CUDA(cudaMemcpyAsync(hb1.data(), hb1_dev, sizeof(double) * (size_t)J * b, cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaMemcpyAsync(hb2.data(), hb2_dev, sizeof(double) * (size_t)J * b, cudaMemcpyDeviceToHost, st));
+    if (int rc = gram_of(wb)) return rc;
+    for (int p = 0; p < b; ++p)
+      for (int q = 0; q < J; ++q) {
+        const double v = hb1[(size_t)q * b + p] + hb2[(size_t)q * b + p];
+        Tat(q, P + p) = v;
+        Tat(P + p, q) = v;
+      }
+    int qr_status = -1;
+    if (int rc = cholqr2(wb, tb, V + (size_t)J * n, &qr_status)) return rc;
+    if (qr_status == 0) {
+      for (int p = 0; p < b; ++p)
+        for (int q = 0; q <= p; ++q) {
+          Tat(J + q, P + p) = Rtot[(size_t)q * b + p];
+          Tat(P + p, J + q) = Rtot[(size_t)q * b + p];
+        }
+      J += b;
+    }
+    // ---- rank-deficient block (an invariant subspace is complete, or an eigenvalue is repeated
+    // more often than the block is wide): one vector at a time, each yields one new basis vector
+    for (int p = 0; p < b && qr_status != 0; ++p) {
       double* w = wb + (size_t)p * n;
       const int col = P + p;
       if (int rc = orthogonalise(w, J, true)) return rc;
       for (int q = 0; q < J; ++q) {
         const double v = hh[q] + hh2[q];
-        Tat(q, col) = v;
-        Tat(col, q) = v;
+        Tat(q, col) += v;
+        if (q != col) Tat(col, q) += v;
       }
       double beta = std::sqrt(nrm2);
       double scale = std::fabs(Tat(col, col));

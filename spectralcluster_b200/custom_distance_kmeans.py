@@ -24,8 +24,8 @@ def run_kmeans(spectral_embeddings, n_clusters: int,
   forms the reference accepts -- any scipy.spatial.distance metric name or callable
   (custom_distance_kmeans.py:37-47; None fails in the reference, and here) -- are host code on the [n, k]
   embeddings (k <= a few dozen columns; the N x N work is long done), exactly like the reference."""
+  eng = dev.Engine.get()          # no CUDA device -> RuntimeError, whatever the metric
   if isinstance(custom_dist, str) and custom_dist in _METRICS:
-    eng = dev.Engine.get()
     t = dev.torch()
     if isinstance(spectral_embeddings, np.ndarray):
       e = t.from_numpy(np.ascontiguousarray(spectral_embeddings, dtype=np.float64)).to(eng.device)

@@ -308,5 +308,14 @@ def test_kmeans_errors():
     scb.custom_distance_kmeans.run_kmeans(e, 3, "cosine", 0)
   with pytest.raises(ValueError):
     scb.custom_distance_kmeans.run_kmeans(e, 11, "cosine", 10)
-  with pytest.raises(NotImplementedError):
-    scb.custom_distance_kmeans.run_kmeans(e, 3, "mahalanobis", 10)
+
+
+@pytest.mark.parametrize("metric", ["cityblock", "chebyshev"])
+def test_kmeans_generic_scipy_metric_matches_oracle(engine, metric):
+  """Any other scipy metric name (custom_distance_kmeans.py:37-47) is the user-hook seam: host
+  arrays in and out on the [n, k] embeddings, like the reference."""
+  rng = np.random.default_rng(3)
+  e = np.vstack([rng.standard_normal((120, 4)) * 0.2 + c for c in ([2, 0, 0, 0], [0, 2, 0, 1], [0, 0, 2, -1])])
+  got = scb.custom_distance_kmeans.run_kmeans(e, 3, metric, 50)
+  want = orc.run_kmeans(e, 3, metric, 50)
+  np.testing.assert_array_equal(got, want)
