@@ -680,6 +680,7 @@ struct UpperArgs {
   __half* lo;
   int64_t ldh;
   int tiles;                 // ceil(n / UT)
+  int run;                   // tile columns per CTA
 };
 
 __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t j, const float (&y)[4],
@@ -713,73 +714,105 @@ __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t 
   }
 }
 
+// One CTA = tile row TI x a run of UP_RUN consecutive tile columns (those with TJ >= TI).  The
+// loads of tile t+1 (four 16-byte rows per thread + the thresholds of its columns) are issued before
+// tile t is thresholded, stored and transposed, so a resident CTA always has a tile in flight --
+// the one-tile-per-CTA form (524,800 CTAs at N = 65,536) exposed the full HBM latency on every
+// tile (ncu: long-scoreboard stalls 8.5 per issue, 50 % of the DRAM peak).
+constexpr int UP_RUN = 8;
+
 __global__ void __launch_bounds__(256)
 k_thrsym_upper(const UpperArgs g) {
   __shared__ float tile[UT][UT + 1];
-  // linear index -> (TI, TJ) with TI <= TJ: row TI of the triangle starts at TI*T - TI(TI-1)/2
-  const int64_t T = g.tiles, idx = blockIdx.x;
-  int64_t ti = (int64_t)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)idx)) * 0.5);
-  while (ti > 0 && ti * T - ti * (ti - 1) / 2 > idx) --ti;
-  while ((ti + 1) * T - (ti + 1) * ti / 2 <= idx) ++ti;
-  const int64_t tj = ti + (idx - (ti * T - ti * (ti - 1) / 2));
-  const int64_t row0 = ti * UT, col0 = tj * UT;
-  const bool diag_tile = (ti == tj);
+  const int64_t ti = blockIdx.y;
+  int64_t tj = (int64_t)blockIdx.x * g.run;
+  const int64_t tj_end = min((int64_t)g.tiles, tj + g.run);
+  if (tj < ti) tj = ti;
+  if (tj >= tj_end) return;                                    // block-uniform
+  const int64_t row0 = ti * UT;
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
-  const int64_t j = col0 + tc;
-  const bool full4 = (j + 3 < g.n);
-  float mj[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  if (full4) {
-    const float4 v = *reinterpret_cast<const float4*>(g.m + j);
-    mj[0] = v.x; mj[1] = v.y; mj[2] = v.z; mj[3] = v.w;
-  } else {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) mj[t] = (j + t < g.n) ? g.m[j + t] : 0.0f;
-  }
-#pragma unroll
-  for (int t = 0; t < 4; ++t) mj[t] *= g.p;
+  float cut_i[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int r = tr + 16 * k;
-    const int64_t i = row0 + r;
-    float y[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (i < g.n) {
-      float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (full4) {
-        const float4 v = ld_stream4(g.b + i * g.ldb + j);
-        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-      } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) bv[t] = (j + t < g.n) ? g.b[i * g.ldb + j + t] : 0.0f;
-      }
-      const float cut_i = g.m[i] * g.p;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float x = bv[t];
-        const float keep = g.binarize ? 1.0f : x;
-        const float small = x * g.mult;
-        const float t1 = (x < cut_i) ? small : keep;
-        const float t2 = (x < mj[t]) ? small : keep;
-        y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
-        if (g.preserve_diag && diag_tile && i == j + t) y[t] = 1.0f;      // refinement.py:208-209
-      }
-      store_y4(g, i, j, y, full4);
-    }
-    if (!diag_tile) {
-      tile[r][tc] = y[0]; tile[r][tc + 1] = y[1]; tile[r][tc + 2] = y[2]; tile[r][tc + 3] = y[3];
-    }
+    const int64_t i = row0 + tr + 16 * k;
+    cut_i[k] = (i < g.n) ? g.m[i] * g.p : 0.0f;
   }
-  if (diag_tile) return;                                       // block-uniform
-  __syncthreads();
-  // transposed write: row (col0 + r') of Y, columns row0 + 4 c' .. +3
-  const int64_t jm = row0 + tc;
-  const bool full4m = (jm + 3 < g.n);
+  float4 cur[4], nxt[4], mcur, mnxt;
+  auto fetch = [&](int64_t t, float4 (&v)[4], float4& mv) {
+    const int64_t j = t * UT + tc;
+    if (j + 3 < g.n) {
+      mv = *reinterpret_cast<const float4*>(g.m + j);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = tr + 16 * k;
-    const int64_t i = col0 + r;
-    if (i >= g.n) continue;
-    const float y[4] = {tile[tc][r], tile[tc + 1][r], tile[tc + 2][r], tile[tc + 3][r]};
-    store_y4(g, i, jm, y, full4m);
+      for (int k = 0; k < 4; ++k) {
+        const int64_t i = row0 + tr + 16 * k;
+        v[k] = (i < g.n) ? ld_stream4(g.b + i * g.ldb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      float tmp[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmp[q] = (j + q < g.n) ? g.m[j + q] : 0.0f;
+      mv = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t i = row0 + tr + 16 * k;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmp[q] = (i < g.n && j + q < g.n) ? g.b[i * g.ldb + j + q] : 0.0f;
+        v[k] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+      }
+    }
+  };
+  fetch(tj, cur, mcur);
+  for (; tj < tj_end; ++tj) {
+    const bool more = tj + 1 < tj_end;
+    if (more) fetch(tj + 1, nxt, mnxt);
+    const int64_t col0 = tj * UT;
+    const bool diag_tile = (ti == tj);
+    const int64_t j = col0 + tc;
+    const bool full4 = (j + 3 < g.n);
+    const float mj[4] = {mcur.x * g.p, mcur.y * g.p, mcur.z * g.p, mcur.w * g.p};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = tr + 16 * k;
+      const int64_t i = row0 + r;
+      float y[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (i < g.n) {
+        const float bv[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float x = bv[t];
+          const float keep = g.binarize ? 1.0f : x;
+          const float small = x * g.mult;
+          const float t1 = (x < cut_i[k]) ? small : keep;
+          const float t2 = (x < mj[t]) ? small : keep;
+          y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
+          if (g.preserve_diag && diag_tile && i == j + t) y[t] = 1.0f;      // refinement.py:208-209
+        }
+        store_y4(g, i, j, y, full4);
+      }
+      if (!diag_tile) {
+        tile[r][tc] = y[0]; tile[r][tc + 1] = y[1]; tile[r][tc + 2] = y[2]; tile[r][tc + 3] = y[3];
+      }
+    }
+    if (!diag_tile) {                                            // block-uniform
+      __syncthreads();
+      // transposed write: row (col0 + r') of Y, columns row0 + 4 c' .. +3
+      const int64_t jm = row0 + tc;
+      const bool full4m = (jm + 3 < g.n);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = tr + 16 * k;
+        const int64_t i = col0 + r;
+        if (i >= g.n) continue;
+        const float y[4] = {tile[tc][r], tile[tc + 1][r], tile[tc + 2][r], tile[tc + 3][r]};
+        store_y4(g, i, jm, y, full4m);
+      }
+      __syncthreads();                                           // the next tile overwrites `tile`
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+      mcur = mnxt;
+    }
   }
 }
 
@@ -1010,9 +1043,15 @@ extern "C" int sc_threshold_symmetrize_upper(sc_context* ctx, const float* b, in
   SC_REQUIRE(!y || vec_ok_f32(y, ldy), "sc_threshold_symmetrize_upper: `y` alignment");
   SC_REQUIRE(!hi || (vec_ok_f16(hi, ldh) && (!lo || vec_ok_f16(lo, ldh))), "sc_threshold_symmetrize_upper: plane alignment");
   g.tiles = (int)((n + UT - 1) / UT);
-  const int64_t pairs = (int64_t)g.tiles * (g.tiles + 1) / 2;
-  SC_REQUIRE(pairs < (1LL << 31), "sc_threshold_symmetrize_upper: n too large for the tile grid");
-  k_thrsym_upper<<<(unsigned)pairs, 256, 0, as_stream(stream)>>>(g); sc::launched();
+  SC_REQUIRE(g.tiles <= 65535, "sc_threshold_symmetrize_upper: n too large for the tile grid");
+  static int run = 0;
+  if (run == 0) {
+    const char* e = getenv("SCB_THRSYM_RUN");
+    run = (e && atoi(e) > 0) ? atoi(e) : UP_RUN;
+  }
+  g.run = run;
+  k_thrsym_upper<<<dim3((unsigned)((g.tiles + run - 1) / run), (unsigned)g.tiles), 256, 0,
+                   as_stream(stream)>>>(g); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -722,6 +723,7 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
         if (int rc = random_direction(p)) return rc;
   }
 
+  const bool trace = std::getenv("SCB_LANCZOS_TRACE") != nullptr;
   int P = 0, J = b;
   int64_t matvecs = 0, restarts = 0, passes = 0;
   int converged = 0, mm = 0;
@@ -755,9 +757,14 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
         for (int q = 0; q < sz; ++q) acc += Tat(sz + i, q) * Z[(size_t)q * sz + p];
         r2 += acc * acc;
       }
-      if (std::sqrt(r2) <= tol * tmax) ++ok;
-      else break;
+      if (trace) fprintf(stderr, "%s%.2e", p ? " " : "[sc lanczos] pass residuals/|theta|max: ", std::sqrt(r2) / tmax);
+      if (std::sqrt(r2) <= tol * tmax) {
+        if (ok == p) ++ok;
+      } else if (!trace) {
+        break;
+      }
     }
+    if (trace) fprintf(stderr, "  (basis %d, converged %d of %d)\n", sz, ok, nev);
     return ok;
   };
 

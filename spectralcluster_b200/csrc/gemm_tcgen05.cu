@@ -86,6 +86,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster run ONE 256 x 256 MMA tile.  The leader
+// (cluster rank 0) issues the MMAs; barriers that the leader waits on live in the leader's shared
+// memory and are addressed from the peer by clearing the CTA-rank bit of the shared::cluster
+// address (the pair occupies ranks 0/1 of the cluster, bit 24 of the window address).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+               ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+// the load lands in THIS CTA's shared memory, its bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int32_t c_inner, int32_t c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -244,15 +288,18 @@ constexpr int NUM_THREADS_V2 = 128 + NUM_EPI_WARPS * 32;   // 384
 //           (tcgen05.ld) and add it, round-to-nearest, into a register-resident 128 x 256 fp32
 //           tile (8 warps x 32 lanes x 128 registers), while the tensor core is already working
 //           on the next chain in the other TMEM buffer.
-template <int PREC>
-struct StageGeom {
-  // planes of one K block in a stage: [A_hi][B_hi][A_lo (PREC>=2)][B_lo (PREC==3)]
-  static constexpr int BYTES = A_PLANE_BYTES * (PREC >= 2 ? 2 : 1) + B_PLANE_BYTES * (PREC == 3 ? 2 : 1);
-  static constexpr int STAGES = PREC == 3 ? 2 : (PREC == 2 ? 3 : 4);
-};
 constexpr int STORE_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;   // 32 KB: one 32x32 fp32 block per epilogue warp
+template <int PREC, int CTAS>
+struct StageGeom {
+  // planes of one K block in a stage: [A_hi][B_hi][A_lo (PREC>=2)][B_lo (PREC==3)]; in a CTA pair
+  // each CTA holds its own 128 rows of A and HALF of the 256 rows of B
+  static constexpr int B_BYTES = B_PLANE_BYTES / CTAS;
+  static constexpr int BYTES = A_PLANE_BYTES * (PREC >= 2 ? 2 : 1) + B_BYTES * (PREC == 3 ? 2 : 1);
+  static constexpr int BUDGET = 227 * 1024 - STORE_STAGE_BYTES - 1024 - 256;
+  static constexpr int STAGES = (BUDGET / BYTES) > 8 ? 8 : (BUDGET / BYTES);
+};
 
-template <int PREC, int EPI, bool SYM>
+template <int PREC, int EPI, bool SYM, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS_V2, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
@@ -264,8 +311,15 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum,
                float* __restrict__ mirror_out, int64_t ldm) {
   constexpr bool SPLIT = PREC >= 2;
-  constexpr int STAGES = StageGeom<PREC>::STAGES;
-  constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
+  constexpr int STAGES = StageGeom<PREC, CTAS>::STAGES;
+  constexpr int STAGE_BYTES = StageGeom<PREC, CTAS>::BYTES;
+  constexpr int B_BYTES = StageGeom<PREC, CTAS>::B_BYTES;
+  // CTA pair: rank r of the cluster takes tile 2 q + r of the enumeration -- the same column block
+  // and the m-blocks (2 j, 2 j + 1), i.e. one 256 x 256 MMA tile per pair (the host only picks
+  // this variant when the number of m-blocks is even, which keeps every pair aligned)
+  const int cta_rank = (CTAS == 2) ? (int)cluster_ctarank() : 0;
+  const int tile_first = (CTAS == 2) ? 2 * ((int)blockIdx.x >> 1) + cta_rank : (int)blockIdx.x;
+  const int tile_stride = (int)gridDim.x;
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
   constexpr int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? 1 : (PREC == 1 ? 4 : 2);
   extern __shared__ uint8_t smem_raw[];
@@ -298,19 +352,27 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS * CTAS);   // the leader hears both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers exist before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -332,14 +394,14 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
         unsigned int passed = 0;
         TileCursor<SYM> cursor;
         cursor.init(tiles_m, tiles_n);
-        for (int round = 0; round * (int)gridDim.x < num_tiles; ++round) {
-          const int tile = round * (int)gridDim.x + (int)blockIdx.x;
+        for (int round = 0; round * tile_stride < num_tiles; ++round) {
+          const int tile = round * tile_stride + tile_first;
           if (tile >= num_tiles) {            // no tile in the last round: keep the targets reachable
             if (pace) atomicAdd(pace, (unsigned int)ck_per_tile);
             continue;
           }
           const TileCoord tc = cursor.at(tile, tab);
-          const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN;
+          const int row_a = tc.m_blk * BM, row_b = tc.n_blk * BN + cta_rank * (BN / CTAS);
           for (int kb = 0; kb < num_kb; ++kb) {
             if (pace && kb % pace_kb == 0) {
               atomicAdd(pace, 1u);
@@ -353,26 +415,44 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
             const uint32_t bar = smem_u32(&full_bar[stage]);
             const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-            mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
             const int k0 = kb * BK;
-            tma_load_2d(base, &map_a_hi, bar, k0, row_a);
-            tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
-            if (PREC >= 2) tma_load_2d(base + A_PLANE_BYTES + B_PLANE_BYTES, &map_a_lo, bar, k0, row_a);
-            if (PREC == 3)
-              tma_load_2d(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES, &map_b_lo, bar, k0, row_b);
+            if (CTAS == 2) {
+              // the leader's barrier counts the bytes of both CTAs' loads
+              if (cta_rank == 0) mbar_expect_tx(bar, (uint32_t)(2 * STAGE_BYTES));
+              tma_load_2d_pair(base, &map_a_hi, bar, k0, row_a);
+              tma_load_2d_pair(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
+              if (PREC >= 2) tma_load_2d_pair(base + A_PLANE_BYTES + B_BYTES, &map_a_lo, bar, k0, row_a);
+              if (PREC == 3)
+                tma_load_2d_pair(base + 2 * A_PLANE_BYTES + B_BYTES, &map_b_lo, bar, k0, row_b);
+            } else {
+              mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
+              tma_load_2d(base, &map_a_hi, bar, k0, row_a);
+              tma_load_2d(base + A_PLANE_BYTES, &map_b_hi, bar, k0, row_b);
+              if (PREC >= 2) tma_load_2d(base + A_PLANE_BYTES + B_BYTES, &map_a_lo, bar, k0, row_a);
+              if (PREC == 3)
+                tma_load_2d(base + 2 * A_PLANE_BYTES + B_BYTES, &map_b_lo, bar, k0, row_b);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     } else if (warp == 1) {
       // ===================================================== MMA issuer
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(BM, BN);
+      if (lane == 0 && cta_rank == 0) {
+        constexpr uint32_t idesc = make_idesc(BM * CTAS, BN);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        auto umma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
+          if (CTAS == 2) umma_f16_pair(d, a, b, id, accumulate);
+          else umma_f16(d, a, b, id, accumulate);
+        };
+        auto commit = [](uint32_t bar) {
+          if (CTAS == 2) umma_commit_pair(bar);
+          else umma_commit(bar);
+        };
+        for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
           for (int kb = 0; kb < num_kb; ++kb) {
             const int in_chunk = kb % CHUNK_KB;
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -385,8 +465,8 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
             const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t a_hi = make_smem_desc(base);
             const uint64_t b_hi = make_smem_desc(base + A_PLANE_BYTES);
-            const uint64_t a_lo = make_smem_desc(base + A_PLANE_BYTES + B_PLANE_BYTES);
-            const uint64_t b_lo = make_smem_desc(base + 2 * A_PLANE_BYTES + B_PLANE_BYTES);
+            const uint64_t a_lo = make_smem_desc(base + A_PLANE_BYTES + B_BYTES);
+            const uint64_t b_lo = make_smem_desc(base + 2 * A_PLANE_BYTES + B_BYTES);
             // The small cross products go first: tcgen05 truncates each accumulate to the
             // accumulator's current ulp, so terms added while the chain is still small cost
             // almost nothing; only the BK/16 hi*hi accumulates run at full magnitude.
@@ -394,25 +474,25 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
               for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
-                umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, (in_chunk | kk) ? 1u : 0u);
-                umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                umma(tmem_d, a_hi + adv, b_lo + adv, idesc, (in_chunk | kk) ? 1u : 0u);
+                umma(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
               }
             } else if (PREC == 2) {
 #pragma unroll
               for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                 const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
-                umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, (in_chunk | kk) ? 1u : 0u);
+                umma(tmem_d, a_lo + adv, b_hi + adv, idesc, (in_chunk | kk) ? 1u : 0u);
               }
             }
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; ++kk) {
               const uint64_t adv = (uint64_t)(kk * UMMA_K * 2 / 16);
-              umma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, (SPLIT || in_chunk || kk) ? 1u : 0u);
+              umma(tmem_d, a_hi + adv, b_hi + adv, idesc, (SPLIT || in_chunk || kk) ? 1u : 0u);
             }
-            umma_commit(smem_u32(&empty_bar[stage]));
+            commit(smem_u32(&empty_bar[stage]));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             if (in_chunk == CHUNK_KB - 1 || kb == num_kb - 1) {
-              umma_commit(smem_u32(&tfull_bar[acc]));            // chain complete
+              commit(smem_u32(&tfull_bar[acc]));            // chain complete
               if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
           }
@@ -428,7 +508,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
     uint32_t acc_phase = 0;
     TileCursor<SYM> cursor;
     cursor.init(tiles_m, tiles_n);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
       const TileCoord tc = cursor.at(tile, tab);
       float sum[128];
 #pragma unroll
@@ -448,7 +528,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_leader(smem_u32(&tempty_bar[acc]));
+          else mbar_arrive(smem_u32(&tempty_bar[acc]));
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       // ---- write-out.  Each thread holds one row x 128 columns; stored straight from registers
@@ -604,11 +687,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // nobody leaves while the peer may still signal it
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                 ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                   ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                   ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -661,17 +750,18 @@ static void build_tile_table(TileTable& tab, int tiles_m, int tiles_n) {
   tab.num_tiles = total;
 }
 
-template <int PREC, int EPI, bool SYM>
+template <int PREC, int EPI, bool SYM, int CTAS>
 static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMap& al,
                   const CUtensorMap& bh, const CUtensorMap& bl, int M, int N, int K, float* C,
                   int64_t ldc, float* rowmax, int diag_shift, float* stat_rowmax,
                   double* stat_rowsum, float* mirror, int64_t ldm, cudaStream_t st) {
-  constexpr int STAGES = StageGeom<PREC>::STAGES;
-  constexpr int STAGE_BYTES = StageGeom<PREC>::BYTES;
+  constexpr int STAGES = StageGeom<PREC, CTAS>::STAGES;
+  constexpr int STAGE_BYTES = StageGeom<PREC, CTAS>::BYTES;
+  static_assert(STAGES >= 2, "tcgen05 GEMM: the operand ring needs at least two stages");
   const size_t smem = (size_t)STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align*/ +
-                      192 /*barriers*/;
+                      256 /*barriers*/;
   SC_REQUIRE(smem <= ctx->smem_optin, "tcgen05 GEMM needs %zu B of shared memory", smem);
-  auto kern = k_gemm_tcgen05<PREC, EPI, SYM>;
+  auto kern = k_gemm_tcgen05<PREC, EPI, SYM, CTAS>;
   SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   TileTable tab = {};
@@ -684,7 +774,8 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   }
   int sms = ctx->sm_count;
   if (ctx->gemm_sm_limit > 0 && ctx->gemm_sm_limit < sms) sms = ctx->gemm_sm_limit;
-  const int grid = tiles < sms ? tiles : sms;
+  int grid = tiles < sms ? tiles : sms;
+  if (CTAS == 2) grid &= ~1;                 // whole CTA pairs (the tile count is even)
   unsigned int* pace = nullptr;
   static int pace_kb = 0;
   if (pace_kb == 0) {
@@ -695,10 +786,39 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     pace = ctx->gemm_pace;
     SC_CUDA(cudaMemsetAsync(pace, 0, sizeof(unsigned int), st));
   }
-  kern<<<grid, NUM_THREADS_V2, smem, st>>>(ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
-                                           pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm); sc::launched();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS_V2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
+                             pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm));
+  sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
+}
+
+// CTA pairs (cta_group::2, one 256 x 256 MMA tile per two SMs: a third less operand traffic from L2
+// and half the B reads from shared memory per SM) whenever the m-blocks pair up; SCB_GEMM_2CTA=0
+// forces the single-CTA kernel.
+static bool want_cta_pair(int M, int prec) {
+  static int mode = -1;                      // 0 never, 1 whenever possible, 2 by precision
+  if (mode < 0) {
+    const char* e = getenv("SCB_GEMM_2CTA");
+    mode = e ? (atoi(e) == 0 ? 0 : 1) : 2;
+  }
+  const int tiles_m = (M + BM - 1) / BM;
+  if (mode == 0 || tiles_m < 2 || tiles_m % 2 != 0) return false;
+  // measured at N = 65,536 (profiles/r02_gemm_2cta.txt): split3 602 vs 659 ms, single 254 vs 255,
+  // split2 458 vs 434 (its 4-stage ring of 48 KB is the better fit without the pair)
+  return mode == 1 || prec != 2;
 }
 
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
@@ -715,9 +835,11 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
   SC_REQUIRE((stat_rowmax == nullptr) == (stat_rowsum == nullptr),
              "tcgen05 GEMM: the row statistics come together");
   const int prec = precision == SC_GEMM_SPLIT3 ? 3 : (precision == SC_GEMM_SPLIT2 ? 2 : 1);
+  const bool pair = want_cta_pair((int)M, prec);
+  const int b_box = pair ? BN / 2 : BN;      // each CTA of a pair loads half of the B tile
   CUtensorMap ah, al, bh, bl;
   if (int r = make_plane_map(&ah, a_hi, M, K, lda, BM)) return r;
-  if (int r = make_plane_map(&bh, b_hi, N, K, ldb, BN)) return r;
+  if (int r = make_plane_map(&bh, b_hi, N, K, ldb, b_box)) return r;
   al = ah;
   bl = bh;
   if (prec >= 2) {
@@ -726,15 +848,20 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
   }
   if (prec == 3) {
     SC_REQUIRE(b_lo, "tcgen05 GEMM: the lo plane of B is missing");
-    if (int r = make_plane_map(&bl, b_lo, N, K, ldb, BN)) return r;
+    if (int r = make_plane_map(&bl, b_lo, N, K, ldb, b_box)) return r;
   }
   const int m = (int)M, n = (int)N, k = (int)K;
   // C = Y Y^T is symmetric when both operands are the same matrix: compute the upper tiles only
   const bool sym = symmetric && a_hi == b_hi && a_lo == b_lo && M == N && lda == ldb;
   SC_REQUIRE(!(sym && mirror), "tcgen05 GEMM: a mirrored copy only makes sense for an off-diagonal block");
-#define SC_TC_LAUNCH(PR, EP, SY)                                                              \
-  return launch<PR, EP, SY>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag, diag_shift, \
-                            stat_rowmax, stat_rowsum, mirror, ldm, st)
+#define SC_TC_LAUNCH(PR, EP, SY)                                                                 \
+  do {                                                                                           \
+    if (pair)                                                                                    \
+      return launch<PR, EP, SY, 2>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag,         \
+                                   diag_shift, stat_rowmax, stat_rowsum, mirror, ldm, st);       \
+    return launch<PR, EP, SY, 1>(ctx, ah, al, bh, bl, m, n, k, C, ldc, rowmax_offdiag,           \
+                                 diag_shift, stat_rowmax, stat_rowsum, mirror, ldm, st);         \
+  } while (0)
 #define SC_TC_PREC(PR)                                                                        \
   do {                                                                                        \
     if (epi == TC_EPI_AFFINITY) { if (sym) SC_TC_LAUNCH(PR, TC_EPI_AFFINITY, true);           \

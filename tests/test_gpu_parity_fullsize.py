@@ -7,7 +7,11 @@
     refinement stage by stage in float64 on the host, LAPACK eigh of the symmetrised matrix
     (SURVEY.md A.2), eigengap and k-means -> eigenvalues within 1e-5 relative (+1e-6 lambda_max
     floor for the Laplacian's lambda_0 ~ 0) AND identical labels;
-  * eigenvalues of exactly block-diagonal affinities (true multiplicity k) against LAPACK.
+  * eigenvalues of exactly block-diagonal affinities (true multiplicity k) against LAPACK;
+  * configs[2] at its REAL size, N = 65,536 (and configs[4]'s N = 32,768 without a Laplacian):
+    the whole chain in float64 torch on the GPU (tests/fp64_checker.py, a checker pinned to the
+    oracle at N = 2,400 by test_fp64_checker_matches_oracle), ARPACK eigenvalues of the
+    symmetrised operator -> eigenvalues within 1e-5 relative AND identical labels.
 """
 
 import numpy as np
@@ -18,6 +22,8 @@ import spectralcluster_b200 as scb
 from spectralcluster_b200 import _native as nat
 from spectralcluster_b200 import device as dev
 from oracle import spectral_oracle as orc
+
+import fp64_checker
 
 pytestmark = pytest.mark.gpu
 
@@ -159,3 +165,59 @@ def test_extremal_solver_finds_every_copy_of_a_repeated_eigenvalue(laplacian, bl
   if laplacian is not None:
     truth = np.repeat(np.arange(blocks), size)
     assert np.array_equal(scb.utils.enforce_ordered_labels(labels), truth)
+
+
+def checker_reference(x, laplacian, max_clusters, device):
+  """eigenvalues, k and labels of the float64 GPU checker (tests/fp64_checker.py)."""
+  s = fp64_checker.refine_through_diffuse(x, device)
+  terms = fp64_checker.operator_terms(s, laplacian)
+  w, v = fp64_checker.extremal_eigh(s, terms, max_clusters + 1)
+  del s
+  if laplacian is None:
+    k, _ = orc.number_of_clusters(w, max_clusters, 1e-2, "ratio", descend=True)
+  else:
+    k, _ = orc.number_of_clusters(w, max_clusters, eigengap="ratio", descend=False)
+  k = max(k, 2)
+  return w, k, orc.run_kmeans(v[:, :k], k)
+
+
+@pytest.mark.parametrize("laplacian,max_clusters,speakers", [(None, 7, 4), ("graphcut", 10, 6)])
+def test_fp64_checker_matches_oracle(engine, laplacian, max_clusters, speakers):
+  """Pins the checker: at N = 2,400 it must reproduce the (reference-pinned) oracle."""
+  n = 2400
+  x = orc.synthetic_dvectors(n, 256, speakers, seed=3)
+  opt = orc.options(min_clusters=2, max_clusters=max_clusters, sequence=orc.ICASSP2018,
+                    laplacian=laplacian)
+  labels_ref, det = orc.predict(x, opt, return_details=True)      # np.linalg.eig, as the reference
+  w_ref = np.asarray(det["eigenvalues"])[:max_clusters + 1]
+  w, k, labels = checker_reference(x, laplacian, max_clusters, engine.device)
+  np.testing.assert_allclose(w, w_ref, rtol=1e-9, atol=1e-11 * np.abs(w_ref).max())
+  assert k == det["n_clusters"]
+  assert np.array_equal(orc.ordered(labels), orc.ordered(labels_ref))
+
+
+@pytest.mark.parametrize("n,laplacian,max_clusters,speakers", [
+    (32768, None, 7, 6),            # configs[4]'s size, ICASSP preset eigen-decomposition
+    (65536, "graphcut", 10, 6)])    # configs[2]: the configuration the metric is quoted on
+def test_configs_at_real_size_vs_float64_checker(engine, n, laplacian, max_clusters, speakers):
+  t = dev.torch()
+  x, truth = orc.synthetic_dvectors(n, 256, speakers, seed=0, return_labels=True)
+  c = scb.SpectralClusterer(
+      min_clusters=2, max_clusters=max_clusters, refinement_options=icassp_options(),
+      laplacian_type=scb.LaplacianType.GraphCut if laplacian else None)
+  labels = c.predict(x)
+  w = np.array(c.last_details["eigenvalues"])
+  k_found = c.last_details["n_clusters"]
+  t.cuda.synchronize()
+  t.cuda.empty_cache()
+  w_ref, k_ref, labels_ref = checker_reference(x, laplacian, max_clusters, engine.device)
+  t.cuda.empty_cache()
+  units = float(np.max(np.abs(w - w_ref) / (1e-5 * np.abs(w_ref) + 1e-6 * np.abs(w_ref).max())))
+  report("config_n%d_%s_fp64_gpu_checker" % (n, laplacian or "nolaplacian"),
+         dict(eigenvalues=w.tolist(), reference=w_ref.tolist(), tolerance_units=units,
+              diffuse_mma_per_product={dev.nat.GEMM_SPLIT3: 3, dev.nat.GEMM_SPLIT2: 2,
+                                       dev.nat.GEMM_SINGLE: 1}[engine.diffuse_precision_for(n)]))
+  assert k_found == k_ref == speakers
+  np.testing.assert_allclose(w, w_ref, rtol=1e-5, atol=1e-6 * np.abs(w_ref).max())
+  assert np.array_equal(scb.utils.enforce_ordered_labels(labels), orc.ordered(labels_ref))
+  assert np.array_equal(scb.utils.enforce_ordered_labels(labels), orc.ordered(truth))
