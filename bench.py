@@ -521,8 +521,9 @@ def main():
   if world > 1:
     # NCCL's own log stays on (the StdoutGuard keeps fd 1 clean for the JSON line): the driver
     # reads the communicator size from it
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+      os.environ["NCCL_DEBUG"] = "INFO"          # images preset VERSION/WARN: the init lines matter
+      os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   eng = dev.Engine.get(local_rank)
   n, d = args.n, args.d

@@ -462,39 +462,17 @@ __device__ __forceinline__ void fast_compute(const BlurArgs& g, const FastCtx<R>
       for (int t = 0; t < HSTRIP; ++t) v = fmaxf(v, b[t]);
       rmax = v;
       // Column maxima of the tile: the lanes of this warp are its 32 rows, each holding the same 16
-      // columns.  Halving butterfly: every step a lane hands half of its columns to the partner
-      // and keeps the maxima of the other half -- 16 shuffles in all instead of 80.
-      float u8[8], u4[4], u2[2], u1;
+      // columns.  The blurred values are non-negative, so their bit patterns order like signed
+      // integers and one REDUX.MAX per column reduces across the warp (16 instructions; the
+      // shuffle butterfly before it took ~95); lane t keeps column t and issues its atomic.
       const int lane = threadIdx.x & 31;
+      float cm = 0.0f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float mine = (lane & 16) ? b[k + 8] : b[k];
-        const float other = (lane & 16) ? b[k] : b[k + 8];
-        u8[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 16));
+      for (int t = 0; t < HSTRIP; ++t) {
+        const int mx = __reduce_max_sync(0xffffffffu, __float_as_int(fmaxf(b[t], 0.0f)));
+        if (lane == t) cm = __int_as_float(mx);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float mine = (lane & 8) ? u8[k + 4] : u8[k];
-        const float other = (lane & 8) ? u8[k] : u8[k + 4];
-        u4[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 8));
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float mine = (lane & 4) ? u4[k + 2] : u4[k];
-        const float other = (lane & 4) ? u4[k] : u4[k + 2];
-        u2[k] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 4));
-      }
-      {
-        const float mine = (lane & 2) ? u2[1] : u2[0];
-        const float other = (lane & 2) ? u2[0] : u2[1];
-        u1 = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 2));
-      }
-      u1 = fmaxf(u1, __shfl_xor_sync(0xffffffffu, u1, 1));
-      if ((lane & 1) == 0) {
-        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                        ((lane >> 1) & 1);
-        atomic_max_nonneg(g.rowmax_out + j0 + col, u1);
-      }
+      if (lane < HSTRIP) atomic_max_nonneg(g.rowmax_out + j0 + lane, cm);
     } else if (EPI == EPI_STORE) {
 #pragma unroll
       for (int q = 0; q < HSTRIP / 4; ++q)
@@ -608,9 +586,24 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
   }
   const float* band_src = g.a + (row0 - R - g.in_row_base) * g.lda - R;   // + col0 per tile
 
+  // tile_is_fast(row0, tx * TTW) for every tile of the band, reduced to four 32-bit compares per
+  // tile (the per-tile form -- a dozen 64-bit compares evaluated twice per tile by every thread --
+  // was 17 % of the kernel's instructions, profiles/r02_blur_source_hotspots.txt): the band-level
+  // conditions once, the first/last tile with a complete halo, and the run of tiles whose halo'd
+  // footprint meets the diagonal.
+  const bool band_fast = (row0 >= R) && (row0 + TTH + R <= g.n) && (row0 + TTH <= g.row_end) &&
+                         ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.a) & 15) == 0);
+  const int tx_fast_max = (g.n >= R + TTW) ? (int)((g.n - R) / TTW) - 1 : -1;   // col0 + TTW + R <= n
+  const int64_t dq = row0 - TTW - 2 * R, dp = row0 + TTH + 2 * R;
+  const int diag_lo = dq < 0 ? 0 : (int)(dq / TTW) + 1;     // first tile with col0 > row0 - TTW - 2R
+  const int diag_hi = (int)((dp - 1) / TTW);                 // last tile with col0 < row0 + TTH + 2R
+  auto is_fast = [&](int tx) {
+    return band_fast && tx >= 1 && tx <= tx_fast_max && (tx < diag_lo || tx > diag_hi);
+  };
+
   auto stage = [&](int tx, float* buf) {
     const int64_t col0 = (int64_t)tx * TTW;
-    if (tile_is_fast<R>(g, row0, col0)) fast_fill<R>(c, band_src + col0, buf);
+    if (is_fast(tx)) fast_fill<R>(c, band_src + col0, buf);
     else tile_fill<R>(g, row0, col0, buf);
   };
   stage(tx0, in0);
@@ -627,7 +620,7 @@ k_blur_band(const BlurArgs g, const BlurWeights bw) {
     }
     __syncthreads();   // tile tx visible; everybody is out of the previous horizontal pass
     const int64_t col0 = (int64_t)tx * TTW;
-    if (tile_is_fast<R>(g, row0, col0)) fast_compute<R, EPI>(g, c, w, col0, cur, mid, rmax);
+    if (is_fast(tx)) fast_compute<R, EPI>(g, c, w, col0, cur, mid, rmax);
     else tile_compute<R, EPI>(g, w, row0, col0, cur, mid, rmax);
   }
   if (EPI == EPI_STATS || EPI == EPI_UPPER) {
@@ -680,7 +673,6 @@ struct UpperArgs {
   __half* lo;
   int64_t ldh;
   int tiles;                 // ceil(n / UT)
-  int run;                   // tile columns per CTA
 };
 
 __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t j, const float (&y)[4],
@@ -714,105 +706,77 @@ __device__ __forceinline__ void store_y4(const UpperArgs& g, int64_t i, int64_t 
   }
 }
 
-// One CTA = tile row TI x a run of UP_RUN consecutive tile columns (those with TJ >= TI).  The
-// loads of tile t+1 (four 16-byte rows per thread + the thresholds of its columns) are issued before
-// tile t is thresholded, stored and transposed, so a resident CTA always has a tile in flight --
-// the one-tile-per-CTA form (524,800 CTAs at N = 65,536) exposed the full HBM latency on every
-// tile (ncu: long-scoreboard stalls 8.5 per issue, 50 % of the DRAM peak).
-constexpr int UP_RUN = 8;
-
+// (A run-based variant -- one CTA per tile row x 8 tile columns, the next tile's loads prefetched
+// into registers -- measured 5.03 ms against 4.55 ms for this one-tile-per-CTA form on the same box
+// at N = 65,536, profiles/r02_ab_stages_one_box.txt: the extra registers cost more occupancy than
+// the prefetch wins.  The limiter is DRAM page locality of the 128-byte transposed row segments.)
 __global__ void __launch_bounds__(256)
 k_thrsym_upper(const UpperArgs g) {
   __shared__ float tile[UT][UT + 1];
-  const int64_t ti = blockIdx.y;
-  int64_t tj = (int64_t)blockIdx.x * g.run;
-  const int64_t tj_end = min((int64_t)g.tiles, tj + g.run);
-  if (tj < ti) tj = ti;
-  if (tj >= tj_end) return;                                    // block-uniform
-  const int64_t row0 = ti * UT;
+  // linear index -> (TI, TJ) with TI <= TJ: row TI of the triangle starts at TI*T - TI(TI-1)/2
+  const int64_t T = g.tiles, idx = blockIdx.x;
+  int64_t ti = (int64_t)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)idx)) * 0.5);
+  while (ti > 0 && ti * T - ti * (ti - 1) / 2 > idx) --ti;
+  while ((ti + 1) * T - (ti + 1) * ti / 2 <= idx) ++ti;
+  const int64_t tj = ti + (idx - (ti * T - ti * (ti - 1) / 2));
+  const int64_t row0 = ti * UT, col0 = tj * UT;
+  const bool diag_tile = (ti == tj);
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
-  float cut_i[4];
+  const int64_t j = col0 + tc;
+  const bool full4 = (j + 3 < g.n);
+  float mj[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (full4) {
+    const float4 v = *reinterpret_cast<const float4*>(g.m + j);
+    mj[0] = v.x; mj[1] = v.y; mj[2] = v.z; mj[3] = v.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) mj[t] = (j + t < g.n) ? g.m[j + t] : 0.0f;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) mj[t] *= g.p;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t i = row0 + tr + 16 * k;
-    cut_i[k] = (i < g.n) ? g.m[i] * g.p : 0.0f;
+    const int r = tr + 16 * k;
+    const int64_t i = row0 + r;
+    float y[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (i < g.n) {
+      float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (full4) {
+        const float4 v = ld_stream4(g.b + i * g.ldb + j);
+        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bv[t] = (j + t < g.n) ? g.b[i * g.ldb + j + t] : 0.0f;
+      }
+      const float cut_i = g.m[i] * g.p;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float x = bv[t];
+        const float keep = g.binarize ? 1.0f : x;
+        const float small = x * g.mult;
+        const float t1 = (x < cut_i) ? small : keep;
+        const float t2 = (x < mj[t]) ? small : keep;
+        y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
+        if (g.preserve_diag && diag_tile && i == j + t) y[t] = 1.0f;      // refinement.py:208-209
+      }
+      store_y4(g, i, j, y, full4);
+    }
+    if (!diag_tile) {
+      tile[r][tc] = y[0]; tile[r][tc + 1] = y[1]; tile[r][tc + 2] = y[2]; tile[r][tc + 3] = y[3];
+    }
   }
-  float4 cur[4], nxt[4], mcur, mnxt;
-  auto fetch = [&](int64_t t, float4 (&v)[4], float4& mv) {
-    const int64_t j = t * UT + tc;
-    if (j + 3 < g.n) {
-      mv = *reinterpret_cast<const float4*>(g.m + j);
+  if (diag_tile) return;                                       // block-uniform
+  __syncthreads();
+  // transposed write: row (col0 + r') of Y, columns row0 + 4 c' .. +3
+  const int64_t jm = row0 + tc;
+  const bool full4m = (jm + 3 < g.n);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t i = row0 + tr + 16 * k;
-        v[k] = (i < g.n) ? ld_stream4(g.b + i * g.ldb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      float tmp[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tmp[q] = (j + q < g.n) ? g.m[j + q] : 0.0f;
-      mv = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t i = row0 + tr + 16 * k;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmp[q] = (i < g.n && j + q < g.n) ? g.b[i * g.ldb + j + q] : 0.0f;
-        v[k] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
-      }
-    }
-  };
-  fetch(tj, cur, mcur);
-  for (; tj < tj_end; ++tj) {
-    const bool more = tj + 1 < tj_end;
-    if (more) fetch(tj + 1, nxt, mnxt);
-    const int64_t col0 = tj * UT;
-    const bool diag_tile = (ti == tj);
-    const int64_t j = col0 + tc;
-    const bool full4 = (j + 3 < g.n);
-    const float mj[4] = {mcur.x * g.p, mcur.y * g.p, mcur.z * g.p, mcur.w * g.p};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = tr + 16 * k;
-      const int64_t i = row0 + r;
-      float y[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (i < g.n) {
-        const float bv[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float x = bv[t];
-          const float keep = g.binarize ? 1.0f : x;
-          const float small = x * g.mult;
-          const float t1 = (x < cut_i[k]) ? small : keep;
-          const float t2 = (x < mj[t]) ? small : keep;
-          y[t] = (g.sym_type == SC_SYMMETRIZE_MAX) ? fmaxf(t1, t2) : 0.5f * (t1 + t2);
-          if (g.preserve_diag && diag_tile && i == j + t) y[t] = 1.0f;      // refinement.py:208-209
-        }
-        store_y4(g, i, j, y, full4);
-      }
-      if (!diag_tile) {
-        tile[r][tc] = y[0]; tile[r][tc + 1] = y[1]; tile[r][tc + 2] = y[2]; tile[r][tc + 3] = y[3];
-      }
-    }
-    if (!diag_tile) {                                            // block-uniform
-      __syncthreads();
-      // transposed write: row (col0 + r') of Y, columns row0 + 4 c' .. +3
-      const int64_t jm = row0 + tc;
-      const bool full4m = (jm + 3 < g.n);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = tr + 16 * k;
-        const int64_t i = col0 + r;
-        if (i >= g.n) continue;
-        const float y[4] = {tile[tc][r], tile[tc + 1][r], tile[tc + 2][r], tile[tc + 3][r]};
-        store_y4(g, i, jm, y, full4m);
-      }
-      __syncthreads();                                           // the next tile overwrites `tile`
-    }
-    if (more) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
-      mcur = mnxt;
-    }
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr + 16 * k;
+    const int64_t i = col0 + r;
+    if (i >= g.n) continue;
+    const float y[4] = {tile[tc][r], tile[tc + 1][r], tile[tc + 2][r], tile[tc + 3][r]};
+    store_y4(g, i, jm, y, full4m);
   }
 }
 
@@ -870,7 +834,10 @@ static int launch_blur(const sc_context* ctx, BlurArgs& g, double sigma, cudaStr
       const char* e = getenv("SCB_BLUR_TILES_PER_CTA");
       tpc_env = e ? atoi(e) : 0;
     }
-    g.tiles_per_cta = tpc_env > 0 ? tpc_env : 4;
+    // measured (profiles/r02_ab_stages_blur_one_box.txt, N = 65,536): the upper-triangle pass takes
+    // 7.14 / 7.42 / 7.69 / 7.99 ms with runs of 2 / 4 / 8 / 16 tiles (shorter runs balance the ragged
+    // band ends of the triangle); the two-pass kernels keep the 4 of r01_blur_tiles_per_cta_sweep.txt
+    g.tiles_per_cta = tpc_env > 0 ? tpc_env : (EPI == EPI_UPPER ? 2 : 4);
     if (g.tiles_per_cta > ntiles) g.tiles_per_cta = ntiles;
     const unsigned gy = (unsigned)((ntiles + g.tiles_per_cta - 1) / g.tiles_per_cta);
     const dim3 grid((unsigned)((g.row_end - g.row_begin + TTH - 1) / TTH), gy);
@@ -1043,15 +1010,9 @@ extern "C" int sc_threshold_symmetrize_upper(sc_context* ctx, const float* b, in
   SC_REQUIRE(!y || vec_ok_f32(y, ldy), "sc_threshold_symmetrize_upper: `y` alignment");
   SC_REQUIRE(!hi || (vec_ok_f16(hi, ldh) && (!lo || vec_ok_f16(lo, ldh))), "sc_threshold_symmetrize_upper: plane alignment");
   g.tiles = (int)((n + UT - 1) / UT);
-  SC_REQUIRE(g.tiles <= 65535, "sc_threshold_symmetrize_upper: n too large for the tile grid");
-  static int run = 0;
-  if (run == 0) {
-    const char* e = getenv("SCB_THRSYM_RUN");
-    run = (e && atoi(e) > 0) ? atoi(e) : UP_RUN;
-  }
-  g.run = run;
-  k_thrsym_upper<<<dim3((unsigned)((g.tiles + run - 1) / run), (unsigned)g.tiles), 256, 0,
-                   as_stream(stream)>>>(g); sc::launched();
+  const int64_t pairs = (int64_t)g.tiles * (g.tiles + 1) / 2;
+  SC_REQUIRE(pairs < (1LL << 31), "sc_threshold_symmetrize_upper: n too large for the tile grid");
+  k_thrsym_upper<<<(unsigned)pairs, 256, 0, as_stream(stream)>>>(g); sc::launched();
   SC_LAUNCH_CHECK();
   return 0;
 }

@@ -194,6 +194,164 @@ static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t l
   }
 }
 
+// ---- v2 of the block product: fp64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA) fed from a
+// 4-stage cp.async ring.  Measured on the B200 (profiles/r02_fp64_rate.txt) DMMA and DFMA have the
+// same peak (37 TFLOP/s), but the DFMA form above needs one 64-bit shared load per 4 FMAs of each
+// lane (shared-memory-bound at 1.2x the FP64 pipe) and keeps only 32 KB of loads in flight per SM
+// (ncu: 2.4 TB/s, 14 TFLOP/s).  Here the S tile is staged in shared memory (108 KB in flight per
+// SM), a B fragment (one T value per lane) serves four row groups, and the FP64 pipe is the only
+// busy unit: 16 vectors' worth of DMMA per 4 columns whatever b <= 16 is.
+//   CTA = 8 warps x 32 rows (4 row groups of 8) = 256 rows; work item = (row block, column split);
+//   stage = 256 rows x 32 columns of S (fp32, row pitch 36 floats: conflict-free A fragments)
+//         + b vectors x 32 columns of T (fp64, row pitch 36 doubles: conflict-free B fragments).
+//   Column splits keep >= ~6 work items per SM; their partial products are summed in a fixed order
+//   by k_symm_reduce (every rank of a sharded run must get bit-identical vectors).
+constexpr int S2_ROWS = 256, S2_COLS = 32, S2_SP = 36, S2_TP = 36, S2_STAGES = 4, S2_MAXB = 16;
+constexpr int S2_S_FLOATS = S2_ROWS * S2_SP;                       // 9,216 floats = 36,864 B
+constexpr int S2_STAGE_BYTES = S2_S_FLOATS * 4 + S2_MAXB * S2_TP * 8;   // + 4,608 B
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_symm_dmma(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
+            const double* __restrict__ t /*[b][ldt]*/, int64_t ldt, int b, int row_blocks,
+            int64_t cols_per_split, double* __restrict__ partial /*[split][b][rows_pad]*/,
+            int64_t rows_pad) {
+  extern __shared__ __align__(16) unsigned char s2_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x % row_blocks, split = blockIdx.x / row_blocks;
+  const int64_t row0 = (int64_t)rb * S2_ROWS;
+  const int64_t c_begin = (int64_t)split * cols_per_split;
+  const int64_t c_end = min(n, c_begin + cols_per_split);
+  const int chunks = (int)((c_end - c_begin + S2_COLS - 1) / S2_COLS);
+  auto stage_s = [&](int st) { return reinterpret_cast<float*>(s2_smem + (size_t)st * S2_STAGE_BYTES); };
+  auto stage_t = [&](int st) {
+    return reinterpret_cast<double*>(s2_smem + (size_t)st * S2_STAGE_BYTES + S2_S_FLOATS * 4);
+  };
+  // fill: 256 rows x 8 16-byte granules of S (8 per thread), b rows x 16 granules of T
+  auto fill = [&](int ch, int st) {
+    const int64_t c0 = c_begin + (int64_t)ch * S2_COLS;
+    float* ss = stage_s(st);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = threadIdx.x + k * 256;           // 0 .. 2047
+      const int r = idx >> 3, q = idx & 7;
+      const int64_t gr = (row0 + r < rows) ? row0 + r : rows - 1;
+      const int64_t gc = c0 + 4 * q;
+      int64_t valid = c_end - gc;
+      valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+      cp_async16_zfill(ss + r * S2_SP + 4 * q, s + gr * lds + (valid > 0 ? gc : 0), (int)valid * 4);
+    }
+    double* ts = stage_t(st);
+    for (int idx = threadIdx.x; idx < b * 16; idx += 256) {
+      const int p = idx >> 4, q = idx & 15;
+      const int64_t gc = c0 + 2 * q;
+      int64_t valid = c_end - gc;
+      valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
+      cp_async16_zfill(ts + p * S2_TP + 2 * q, t + (int64_t)p * ldt + (valid > 0 ? gc : 0), (int)valid * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) acc[g][h][0] = acc[g][h][1] = 0.0;
+  const int fr = lane >> 2, fk = lane & 3;
+  const bool n1_live = (8 + fr) < b;                    // second n-tile: vectors 8..15
+  const bool n0_live = fr < b;
+#pragma unroll
+  for (int st = 0; st < S2_STAGES - 1; ++st) {
+    if (st < chunks) fill(st, st);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int ch = 0; ch < chunks; ++ch) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(S2_STAGES - 2) : "memory");
+    __syncthreads();                                    // chunk ch landed; stage (ch-1)%S is free
+    if (ch + S2_STAGES - 1 < chunks) fill(ch + S2_STAGES - 1, (ch + S2_STAGES - 1) % S2_STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* ss = stage_s(ch % S2_STAGES) + (warp * 32 + fr) * S2_SP + fk;
+    const double* ts = stage_t(ch % S2_STAGES) + fk;
+#pragma unroll
+    for (int ks = 0; ks < S2_COLS / 4; ++ks) {
+      const double b0 = n0_live ? ts[fr * S2_TP + 4 * ks] : 0.0;
+      const double b1 = n1_live ? ts[(8 + fr) * S2_TP + 4 * ks] : 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const double a = (double)ss[g * 8 * S2_SP + 4 * ks];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(acc[g][0][0]), "+d"(acc[g][0][1]) : "d"(a), "d"(b0));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(acc[g][1][0]), "+d"(acc[g][1][1]) : "d"(a), "d"(b1));
+      }
+    }
+  }
+  // C fragment: row = fr of the group, vectors 8 h + 2 fk + {0, 1}
+  double* out = partial + (int64_t)split * b * rows_pad;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int64_t row = row0 + warp * 32 + g * 8 + fr;
+    if (row >= rows) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int p = 8 * h + 2 * fk + e;
+        if (p < b) out[(int64_t)p * rows_pad + row] = acc[g][h][e];
+      }
+  }
+}
+
+// y[p][row] = sum over the column splits, in order
+__global__ void k_symm_reduce(const double* __restrict__ partial, int splits, int b, int64_t rows,
+                              int64_t rows_pad, double* __restrict__ y, int64_t ldy) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (row >= rows) return;
+  double acc = 0.0;
+  for (int sp = 0; sp < splits; ++sp) acc += partial[((int64_t)sp * b + p) * rows_pad + row];
+  y[(int64_t)p * ldy + row] = acc;
+}
+
+// scratch the caller provides for the v2 product: doubles
+static size_t symm_v2_scratch_doubles(int64_t rows, int64_t n, int b, int sm_count, int* splits_out,
+                                      int64_t* cols_per_split_out) {
+  const int64_t row_blocks = (rows + S2_ROWS - 1) / S2_ROWS;
+  int64_t splits = (6LL * sm_count + row_blocks - 1) / row_blocks;
+  const int64_t max_splits = (n + 2047) / 2048;           // at least 2,048 columns per work item
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int64_t cps = (n + splits - 1) / splits;
+  cps = (cps + S2_COLS - 1) / S2_COLS * S2_COLS;
+  splits = (n + cps - 1) / cps;
+  *splits_out = (int)splits;
+  *cols_per_split_out = cps;
+  const int64_t rows_pad = (rows + 1) & ~(int64_t)1;
+  return (size_t)splits * b * rows_pad;
+}
+
+static int launch_symm_v2(int b, const float* s, int64_t rows, int64_t n, int64_t lds, const double* t,
+                          int64_t ldt, double* y, int64_t ldy, double* scratch, int splits,
+                          int64_t cols_per_split, cudaStream_t st) {
+  SC_REQUIRE(b >= 1 && b <= S2_MAXB && ldt % 2 == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 &&
+             lds % 4 == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0,
+             "sc_eigh_extremal: internal (block product alignment)");
+  const int row_blocks = (int)((rows + S2_ROWS - 1) / S2_ROWS);
+  const int64_t rows_pad = (rows + 1) & ~(int64_t)1;
+  const size_t smem = (size_t)S2_STAGES * S2_STAGE_BYTES;
+  SC_CUDA(cudaFuncSetAttribute(k_symm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_symm_dmma<<<(unsigned)(row_blocks * splits), 256, smem, st>>>(s, rows, n, lds, t, ldt, b, row_blocks,
+                                                               cols_per_split, scratch, rows_pad);
+  sc::launched();
+  k_symm_reduce<<<dim3((unsigned)((rows + 255) / 256), (unsigned)b), 256, 0, st>>>(scratch, splits, b, rows,
+                                                                                 rows_pad, y, ldy);
+  sc::launched();
+  return 0;
+}
+
 // t_p = c .* x_p for the vectors p = blockIdx.y of a block (contiguous, stride n)
 __global__ void k_prescale(const double* __restrict__ x, const double* __restrict__ left,
                            const double* __restrict__ right, int64_t n, double* __restrict__ t,
@@ -724,6 +882,20 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   }
 
   const bool trace = std::getenv("SCB_LANCZOS_TRACE") != nullptr;
+  // block product: DMMA kernel (v2) unless SCB_SYMM_V2=0
+  static int symm_v2_mode = -1;
+  if (symm_v2_mode < 0) {
+    const char* e = std::getenv("SCB_SYMM_V2");
+    symm_v2_mode = (e && std::atoi(e) == 0) ? 0 : 1;
+  }
+  const bool symm_v2 = symm_v2_mode == 1;
+  int v2_splits = 1;
+  int64_t v2_cols = n;
+  Scratch v2buf;
+  if (symm_v2) {
+    const size_t need = symm_v2_scratch_doubles(rows, n, b, ctx->sm_count, &v2_splits, &v2_cols);
+    SC_CUDA(v2buf.alloc(sizeof(double) * need, st));
+  }
   int P = 0, J = b;
   int64_t matvecs = 0, restarts = 0, passes = 0;
   int converged = 0, mm = 0;
@@ -771,7 +943,12 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   for (;;) {
     // ---- one pass over S: W = flip * Op V[P..P+b)
     k_prescale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, left, right, n, tb, ldtb); sc::launched();
-    if (int rc = launch_symm(b, s, rows, n, lds, tb, ldtb, y_mine, y_slab_len, st)) return rc;
+    if (symm_v2) {
+      if (int rc = launch_symm_v2(b, s, rows, n, lds, tb, ldtb, y_mine, y_slab_len, v2buf.as<double>(),
+                                  v2_splits, v2_cols, st)) return rc;
+    } else {
+      if (int rc = launch_symm(b, s, rows, n, lds, tb, ldtb, y_mine, y_slab_len, st)) return rc;
+    }
     SC_LAUNCH_CHECK();
     if (gather) SC_REQUIRE(gather(user, b) == 0, "sc_eigh_extremal_sharded: the gather callback failed");
     k_postscale<<<dim3(gn, b), 256, 0, st>>>(V + (size_t)P * n, y_base, y_slab_len, b, delta, left,

@@ -808,17 +808,20 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
 // CTA pairs (cta_group::2, one 256 x 256 MMA tile per two SMs: a third less operand traffic from L2
 // and half the B reads from shared memory per SM) whenever the m-blocks pair up; SCB_GEMM_2CTA=0
 // forces the single-CTA kernel.
-static bool want_cta_pair(int M, int prec) {
-  static int mode = -1;                      // 0 never, 1 whenever possible, 2 by precision
+static bool want_cta_pair(int M, int K, int prec) {
+  static int mode = -1;                      // 0 never, 1 whenever possible, 2 measured policy
   if (mode < 0) {
     const char* e = getenv("SCB_GEMM_2CTA");
     mode = e ? (atoi(e) == 0 ? 0 : 1) : 2;
   }
   const int tiles_m = (M + BM - 1) / BM;
   if (mode == 0 || tiles_m < 2 || tiles_m % 2 != 0) return false;
-  // measured at N = 65,536 (profiles/r02_gemm_2cta.txt): split3 602 vs 659 ms, single 254 vs 255,
-  // split2 458 vs 434 (its 4-stage ring of 48 KB is the better fit without the pair)
-  return mode == 1 || prec != 2;
+  // Measured (profiles/r02_gemm_2cta.txt, r02_ab_stages_one_box.txt): the pair wins where the four
+  // operand planes of the three-MMA split crowd L2 and shared memory -- N = K = 65,536: 602 vs
+  // 659 ms -- and loses a few per cent where a single MMA per stage is already power-bound
+  // (single: 228 vs 223 ms in predict(); split2: 458 vs 434 ms) and on the short-K affinity
+  // (K = 256: 5.7 vs 5.25 ms).
+  return mode == 1 || (prec == 3 && K >= 2048);
 }
 
 int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half* a_hi,
@@ -835,7 +838,7 @@ int gemm_nt_tcgen05(const sc_context* ctx, int epi, int precision, const __half*
   SC_REQUIRE((stat_rowmax == nullptr) == (stat_rowsum == nullptr),
              "tcgen05 GEMM: the row statistics come together");
   const int prec = precision == SC_GEMM_SPLIT3 ? 3 : (precision == SC_GEMM_SPLIT2 ? 2 : 1);
-  const bool pair = want_cta_pair((int)M, prec);
+  const bool pair = want_cta_pair((int)M, (int)K, prec);
   const int b_box = pair ? BN / 2 : BN;      // each CTA of a pair loads half of the B tile
   CUtensorMap ah, al, bh, bl;
   if (int r = make_plane_map(&ah, a_hi, M, K, lda, BM)) return r;
