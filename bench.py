@@ -53,9 +53,10 @@ def parse():
                   help="auto: predict on 1 GPU, sharded-predict (ONE problem, strong scaling) on "
                        "more; replicas: one independent batch per GPU; sharded-refine: configs[3], "
                        "timed region = affinity -> ... -> Diffuse -> row statistics (no eigensolve)")
-  ap.add_argument("--cpu-stagewise-n", type=int, default=0,
-                  help="--impl reference: also time the CPU path stage by stage at this N "
-                       "(BASELINE.md section 3 planned 16384; 0 = skip)")
+  ap.add_argument("--cpu-stagewise-n", type=int, default=8192,
+                  help="--impl reference: also time the CPU path stage by stage at this N, once, "
+                       "outside the timed steps (BASELINE.md section 3 planned 16384: ~70 s; the "
+                       "default 8192 takes ~15 s; 0 = skip)")
   return ap.parse_args()
 
 
@@ -484,9 +485,10 @@ class StdoutGuard:
   def result(self, line: str):
     sys.stdout.flush()
     os.dup2(self.saved, 1)
-    os.close(self.saved)
     sys.stdout.write(line + "\n")
     sys.stdout.flush()
+    # ... and back to stderr: with NCCL_DEBUG=INFO the communicator teardown logs on fd 1 too
+    os.dup2(2, 1)
 
 
 GUARD = None

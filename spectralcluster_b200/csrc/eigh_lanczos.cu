@@ -206,7 +206,7 @@ static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t l
 //         + b vectors x 32 columns of T (fp64, row pitch 36 doubles: conflict-free B fragments).
 //   Column splits keep >= ~6 work items per SM; their partial products are summed in a fixed order
 //   by k_symm_reduce (every rank of a sharded run must get bit-identical vectors).
-constexpr int S2_ROWS = 256, S2_COLS = 32, S2_SP = 36, S2_TP = 36, S2_STAGES = 4, S2_MAXB = 16;
+constexpr int S2_ROWS = 256, S2_COLS = 32, S2_SP = 36, S2_TP = 36, S2_MAXB = 16;
 constexpr int S2_S_FLOATS = S2_ROWS * S2_SP;                       // 9,216 floats = 36,864 B
 constexpr int S2_STAGE_BYTES = S2_S_FLOATS * 4 + S2_MAXB * S2_TP * 8;   // + 4,608 B
 
@@ -215,7 +215,8 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+template <int S2_STAGES>       // 4 stages: one CTA per SM; 2 stages: two CTAs per SM (16 warps)
+__global__ void __launch_bounds__(256, S2_STAGES <= 2 ? 2 : 1)
 k_symm_dmma(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
             const double* __restrict__ t /*[b][ldt]*/, int64_t ldt, int b, int row_blocks,
             int64_t cols_per_split, double* __restrict__ partial /*[split][b][rows_pad]*/,
@@ -341,10 +342,16 @@ static int launch_symm_v2(int b, const float* s, int64_t rows, int64_t n, int64_
              "sc_eigh_extremal: internal (block product alignment)");
   const int row_blocks = (int)((rows + S2_ROWS - 1) / S2_ROWS);
   const int64_t rows_pad = (rows + 1) & ~(int64_t)1;
-  const size_t smem = (size_t)S2_STAGES * S2_STAGE_BYTES;
-  SC_CUDA(cudaFuncSetAttribute(k_symm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_symm_dmma<<<(unsigned)(row_blocks * splits), 256, smem, st>>>(s, rows, n, lds, t, ldt, b, row_blocks,
-                                                               cols_per_split, scratch, rows_pad);
+  static int stages = 0;
+  if (stages == 0) {
+    const char* e = getenv("SCB_SYMM_STAGES");
+    stages = (e && atoi(e) == 2) ? 2 : 4;
+  }
+  const size_t smem = (size_t)stages * S2_STAGE_BYTES;
+  auto kern = stages == 2 ? k_symm_dmma<2> : k_symm_dmma<4>;
+  SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(row_blocks * splits), 256, smem, st>>>(s, rows, n, lds, t, ldt, b, row_blocks,
+                                                         cols_per_split, scratch, rows_pad);
   sc::launched();
   k_symm_reduce<<<dim3((unsigned)((rows + 255) / 256), (unsigned)b), 256, 0, st>>>(scratch, splits, b, rows,
                                                                                  rows_pad, y, ldy);

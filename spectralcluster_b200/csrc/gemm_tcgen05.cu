@@ -309,7 +309,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
                float* __restrict__ C, int64_t ldc, float* __restrict__ rowmax_offdiag,
                int diag_shift, unsigned int* __restrict__ pace, int pace_kb,
                float* __restrict__ stat_rowmax, double* __restrict__ stat_rowsum,
-               float* __restrict__ mirror_out, int64_t ldm) {
+               float* __restrict__ mirror_out, int64_t ldm, int aff_chunk_kb) {
   constexpr bool SPLIT = PREC >= 2;
   constexpr int STAGES = StageGeom<PREC, CTAS>::STAGES;
   constexpr int STAGE_BYTES = StageGeom<PREC, CTAS>::BYTES;
@@ -321,7 +321,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
   const int tile_first = (CTAS == 2) ? 2 * ((int)blockIdx.x >> 1) + cta_rank : (int)blockIdx.x;
   const int tile_stride = (int)gridDim.x;
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
-  constexpr int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? 1 : (PREC == 1 ? 4 : 2);
+  // K blocks per TMEM chain.  Diffuse: 2 (split) / 4 (single).  Affinity (K = d): `aff_chunk_kb`
+  // from the host -- 2 makes a d = 256 tile exactly two chains, one per TMEM buffer, so the tensor
+  // core runs the NEXT tile while the epilogue warps write this one out (with chains of 1 the MMA
+  // warp stalls on TMEM half-way through the next tile and ~1/3 of the kernel was un-overlapped
+  // MMA time)
+  const int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? aff_chunk_kb : (PREC == 1 ? 4 : 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -798,8 +803,13 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int aff_chunk_kb = 0;
+  if (aff_chunk_kb == 0) {
+    const char* e = getenv("SCB_AFFINITY_CHUNK_KB");
+    aff_chunk_kb = (e && atoi(e) > 0) ? atoi(e) : 2;
+  }
   SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
-                             pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm));
+                             pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm, aff_chunk_kb));
   sc::launched();
   SC_LAUNCH_CHECK();
   return 0;

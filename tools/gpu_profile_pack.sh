@@ -15,10 +15,12 @@ timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file $out/${tag}_l
 python tools/summarize_launches.py $out/${tag}_launches_n${n}.csv > $out/${tag}_launches_n${n}.txt 2>&1
 
 # 2. full captures: refinement pair, both GEMMs, the block matvec
-timeout 900 $NCU --set full --import-source on -k regex:'k_blur_band|k_thrsym_upper|k_gemm_tcgen05|k_symm_f32_f64|k_symv_f32_f64' \
-  -c 6 -o $out/${tag}_full_n${n} -f python tools/profile_step.py --n $n > $out/${tag}_full_n${n}.log 2>&1
+timeout 900 $NCU --set full --import-source on -k regex:'k_blur_band|k_thrsym_upper|k_gemm_tcgen05|k_symm_dmma|k_symm_f32_f64|k_block_proj' \
+  -c 7 -o $out/${tag}_full_n${n} -f python tools/profile_step.py --n $n > $out/${tag}_full_n${n}.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full_n${n}.ncu-rep > $out/${tag}_ncu_full_n${n}.txt 2>&1
 
-# 3. MMAs per Diffuse product vs parity
-timeout 900 python tools/diffuse_precision_study.py > $out/${tag}_diffuse_precision.md 2> $out/${tag}_diffuse_precision.err
+# 3. MMAs per Diffuse product vs parity (only on request: PRECISION_STUDY=1)
+if [ "$PRECISION_STUDY" = "1" ]; then
+  timeout 900 python tools/diffuse_precision_study.py > $out/${tag}_diffuse_precision.md 2> $out/${tag}_diffuse_precision.err
+fi
 tail -5 $out/${tag}_launches_n${n}.txt
