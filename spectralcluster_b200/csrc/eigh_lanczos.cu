@@ -195,7 +195,7 @@ static int launch_symm(int p, const float* s, int64_t rows, int64_t n, int64_t l
 }
 
 // ---- v2 of the block product: fp64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA) fed from a
-// 4-stage cp.async ring.  Measured on the B200 (profiles/r02_fp64_rate.txt) DMMA and DFMA have the
+// cp.async ring (2 stages x 2 CTAs per SM).  Measured on the B200 (profiles/r02_fp64_rate.txt) DMMA and DFMA have the
 // same peak (37 TFLOP/s), but the DFMA form above needs one 64-bit shared load per 4 FMAs of each
 // lane (shared-memory-bound at 1.2x the FP64 pipe) and keeps only 32 KB of loads in flight per SM
 // (ncu: 2.4 TB/s, 14 TFLOP/s).  Here the S tile is staged in shared memory (108 KB in flight per
@@ -215,7 +215,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 
-template <int S2_STAGES>       // 4 stages: one CTA per SM; 2 stages: two CTAs per SM (16 warps)
+template <int S2_STAGES>       // 2 stages: two CTAs per SM (16 warps, the default); 4: one CTA per SM
 __global__ void __launch_bounds__(256, S2_STAGES <= 2 ? 2 : 1)
 k_symm_dmma(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
             const double* __restrict__ t /*[b][ldt]*/, int64_t ldt, int b, int row_blocks,
@@ -264,6 +264,7 @@ k_symm_dmma(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
   const int fr = lane >> 2, fk = lane & 3;
   const bool n1_live = (8 + fr) < b;                    // second n-tile: vectors 8..15
   const bool n0_live = fr < b;
+  const bool two_tiles = b > 8;                         // block-uniform
 #pragma unroll
   for (int st = 0; st < S2_STAGES - 1; ++st) {
     if (st < chunks) fill(st, st);
@@ -285,8 +286,9 @@ k_symm_dmma(const float* __restrict__ s, int64_t rows, int64_t n, int64_t lds,
         const double a = (double)ss[g * 8 * S2_SP + 4 * ks];
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                      : "+d"(acc[g][0][0]), "+d"(acc[g][0][1]) : "d"(a), "d"(b0));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                     : "+d"(acc[g][1][0]), "+d"(acc[g][1][1]) : "d"(a), "d"(b1));
+        if (two_tiles)                                  // b <= 8: the second n-tile would be all zeros
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[g][1][0]), "+d"(acc[g][1][1]) : "d"(a), "d"(b1));
       }
     }
   }
@@ -345,7 +347,7 @@ static int launch_symm_v2(int b, const float* s, int64_t rows, int64_t n, int64_
   static int stages = 0;
   if (stages == 0) {
     const char* e = getenv("SCB_SYMM_STAGES");
-    stages = (e && atoi(e) == 2) ? 2 : 4;
+    stages = (e && atoi(e) == 4) ? 4 : 2;    // measured: 18.4 vs 21.3 ms per solve at N = 65,536
   }
   const size_t smem = (size_t)stages * S2_STAGE_BYTES;
   auto kern = stages == 2 ? k_symm_dmma<2> : k_symm_dmma<4>;

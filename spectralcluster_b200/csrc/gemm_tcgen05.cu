@@ -322,10 +322,12 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a_hi,
   const int tile_stride = (int)gridDim.x;
   // K blocks per TMEM chain; the affinity (K = d, output-bound) can afford the shortest chain
   // K blocks per TMEM chain.  Diffuse: 2 (split) / 4 (single).  Affinity (K = d): `aff_chunk_kb`
-  // from the host -- 2 makes a d = 256 tile exactly two chains, one per TMEM buffer, so the tensor
-  // core runs the NEXT tile while the epilogue warps write this one out (with chains of 1 the MMA
-  // warp stalls on TMEM half-way through the next tile and ~1/3 of the kernel was un-overlapped
-  // MMA time)
+  // from the host, 1 by default.  Chains of 2 make a d = 256 tile exactly two chains, one per TMEM
+  // buffer, so the tensor core runs the NEXT tile while the epilogue warps write this one out:
+  // 5.3 -> 4.35 ms at N = 65,536 (profiles/r02_ab_stages_affchain_symmstages_one_box.txt) -- but
+  // the 8 extra truncating accumulates push 4 of 1.8 M test elements to 4.5 fp32 ulps from the
+  // float64 oracle (bar: 4), and the affinity feeds a threshold, so the faster setting stays an
+  // opt-in (SCB_AFFINITY_CHUNK_KB=2).
   const int CHUNK_KB = (EPI == TC_EPI_AFFINITY) ? aff_chunk_kb : (PREC == 1 ? 4 : 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -806,7 +808,7 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
   static int aff_chunk_kb = 0;
   if (aff_chunk_kb == 0) {
     const char* e = getenv("SCB_AFFINITY_CHUNK_KB");
-    aff_chunk_kb = (e && atoi(e) > 0) ? atoi(e) : 2;
+    aff_chunk_kb = (e && atoi(e) > 0) ? atoi(e) : 1;
   }
   SC_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, tab, M, N, K, C, ldc, rowmax, diag_shift,
                              pace, pace_kb, stat_rowmax, stat_rowsum, mirror, ldm, aff_chunk_kb));

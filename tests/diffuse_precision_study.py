@@ -50,7 +50,7 @@ def relerr(w, ref):
 def main():
   eng = dev.Engine.get()
   t = dev.torch()
-  print("# Diffuse: MMAs per product vs parity (tools/diffuse_precision_study.py)\n")
+  print("# Diffuse: MMAs per product vs parity (tests/diffuse_precision_study.py)\n")
   print("## N=2,400 against the float64 oracle (eigenvalue error in units of the parity tolerance: max |dw| / (1e-5 |w| + 1e-6 max|w|); <= 1 passes)\n")
   print("| config | seed | " + " | ".join("%s eig err / labels" % m for m, _ in MODES) + " |")
   print("|---|---|" + "---|" * len(MODES))

@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-(time timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_predict.py tests/test_gpu_fullsize.py tests/test_gpu_sharded.py tests/test_gpu_callers.py tests/test_gpu_constraints.py -m gpu -q --durations=5) > gpurun_out/r02_gputest6.log 2>&1; echo TESTRC=$? >> gpurun_out/r02_gputest6.log
-o=gpurun_out/r02_ab_stages4.txt; : > $o
-for rep in 1 2; do
-  timeout 200 python tools/time_stages.py --tag "default(rep$rep)" >> $o 2>&1
-  SCB_AFFINITY_CHUNK_KB=1 timeout 200 python tools/time_stages.py --tag "aff-chain1(rep$rep)" >> $o 2>&1
-  SCB_SYMM_STAGES=2 timeout 200 python tools/time_stages.py --tag "symm-2stage-2cta(rep$rep)" >> $o 2>&1
-done
-tail -4 gpurun_out/r02_gputest6.log; cat $o
+(time timeout 1100 python -m pytest tests -m gpu -x -q --durations=10) > gpurun_out/r02_gputest_final.log 2>&1; echo TESTRC=$? >> gpurun_out/r02_gputest_final.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.txt 2>&1
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err
+bash tools/gpu_profile_pack.sh r02f 65536
+tail -4 gpurun_out/r02_gputest_final.log; cat gpurun_out/r02_smoke.txt | tail -2; head -c 600 gpurun_out/r02_bench_final.json

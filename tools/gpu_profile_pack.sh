@@ -21,6 +21,6 @@ python tools/ncu_summary.py $out/${tag}_full_n${n}.ncu-rep > $out/${tag}_ncu_ful
 
 # 3. MMAs per Diffuse product vs parity (only on request: PRECISION_STUDY=1)
 if [ "$PRECISION_STUDY" = "1" ]; then
-  timeout 900 python tools/diffuse_precision_study.py > $out/${tag}_diffuse_precision.md 2> $out/${tag}_diffuse_precision.err
+  timeout 900 python tests/diffuse_precision_study.py > $out/${tag}_diffuse_precision.md 2> $out/${tag}_diffuse_precision.err
 fi
 tail -5 $out/${tag}_launches_n${n}.txt
