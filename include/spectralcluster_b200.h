@@ -283,6 +283,15 @@ int sc_eigh_extremal_sharded(sc_context* ctx, const float* s_block, int64_t rows
                              int slab, int64_t slab_len, sc_gather_fn gather, void* user,
                              double* w_host, double* v_dev, int64_t* stats_host, void* stream);
 
+/* The block product of the extremal solver on its own (the O(N^2) part of what replaces
+ * np.linalg.eig at utils.py:59): y[p][0..rows) = s[0..rows, 0..n) t[p][0..n) for p < b <= 16; `s` fp32
+ * row-major (16-byte aligned, lds % 4 == 0), `t` / `y` fp64 vector-major with leading dimensions
+ * ldt (even, t 16-byte aligned) / ldy.  One pass over `s`; products on the fp64 tensor cores,
+ * column splits summed in a fixed order (bit-reproducible).  Used by sc_eigh_extremal[_sharded];
+ * exported so that the kernel has its own parity test against a float64 product. */
+int sc_block_product(sc_context* ctx, const float* s, int64_t rows, int64_t n, int64_t lds,
+                     const double* t, int64_t ldt, int b, double* y, int64_t ldy, void* stream);
+
 /* ---- Krylov primitives of the general (non-symmetrisable) eigen path: utils.py:59-61 is
  * np.linalg.eig + .real; sequences such as [RowWiseThreshold] alone leave a genuinely
  * non-symmetric matrix.  The Krylov-Schur recurrence is host logic

@@ -82,6 +82,8 @@ PROTOTYPES = {
     "sc_eigh_extremal_sharded": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
                                  c_dbl, c_int, c_i64, c_i64, c_dbl, c_i64, c_ptr, c_int, c_i64,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sc_block_product": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, ctypes.c_int, c_ptr, c_i64,
+                         c_ptr],
     "sc_krylov_matvec": [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "sc_krylov_orthogonalize": [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "sc_krylov_scale": [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr],

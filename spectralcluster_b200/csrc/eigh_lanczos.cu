@@ -1080,6 +1080,21 @@ static int lanczos_impl(sc_context* ctx, const float* s, int64_t rows, int64_t r
   return 0;
 }
 
+extern "C" int sc_block_product(sc_context* ctx, const float* s, int64_t rows, int64_t n, int64_t lds,
+                                const double* t, int64_t ldt, int b, double* y, int64_t ldy,
+                                void* stream) {
+  SC_REQUIRE(ctx && s && t && y && rows > 0 && n > 0 && b >= 1 && b <= S2_MAXB && ldt >= n && ldy >= rows,
+             "sc_block_product: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  int splits = 1;
+  int64_t cols = n;
+  Scratch buf;
+  SC_CUDA(buf.alloc(sizeof(double) * symm_v2_scratch_doubles(rows, n, b, ctx->sm_count, &splits, &cols), st));
+  if (int rc = launch_symm_v2(b, s, rows, n, lds, t, ldt, y, ldy, buf.as<double>(), splits, cols, st)) return rc;
+  SC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int sc_eigh_block_size(int64_t n_values) {
   return n_values <= 4 ? 4 : (n_values <= 8 ? 8 : (n_values <= 12 ? 12 : 16));
 }

@@ -319,3 +319,29 @@ def test_kmeans_generic_scipy_metric_matches_oracle(engine, metric):
   got = scb.custom_distance_kmeans.run_kmeans(e, 3, metric, 50)
   want = orc.run_kmeans(e, 3, metric, 50)
   np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("rows,n,b", [(1, 7, 1), (255, 33, 4), (256, 1000, 8), (1000, 1000, 12),
+                                      (2304, 2304, 16), (777, 4099, 11), (8192, 16384, 12)])
+def test_block_product_vs_float64(engine, rows, n, b):
+  """sc_block_product (fp64 DMMA, cp.async ring, column splits) against the float64 product of the
+  same fp32 matrix: ragged rows / columns / block widths; bit-reproducible from run to run."""
+  import ctypes
+  t = dev.torch()
+  g = t.Generator(device="cpu").manual_seed(rows * 31 + n)
+  ld = dev.round_up(n, 64)
+  s = t.full((rows, ld), float("nan"), dtype=t.float32)          # the padding must never be read
+  s[:, :n] = t.rand((rows, n), generator=g) - 0.3
+  ldt = n + (n & 1) + 2
+  tv = t.randn((b, ldt), generator=g, dtype=t.float64)
+  s_d, t_d = s.to(engine.device), tv.to(engine.device)
+  outs = []
+  for _ in range(2):
+    y = t.zeros((b, rows), dtype=t.float64, device=engine.device)
+    engine.call("sc_block_product", dev._ptr(s_d), rows, n, ld, dev._ptr(t_d), ldt, ctypes.c_int(b),
+                dev._ptr(y), rows, engine.stream)
+    outs.append(y.cpu())
+  want = tv[:, :n] @ s[:, :n].double().T
+  scale = (tv[:, :n].abs() @ s[:, :n].double().abs().T).clamp_min(1e-300)
+  assert float(((outs[0] - want).abs() / scale).max()) <= 1e-14
+  assert t.equal(outs[0], outs[1])
