@@ -65,7 +65,8 @@ extern "C" int sc_context_create(int device, sc_context** out) {
   ctx->cc_minor = prop.minor;
   ctx->gemm_sm_limit = 0;
   ctx->gemm_pace = nullptr;
-  if (!getenv("SCB_NO_GEMM_PACING") && cudaMalloc(&ctx->gemm_pace, sizeof(unsigned int)) != cudaSuccess)
+  if (!getenv("SCB_NO_GEMM_PACING") &&
+      cudaMalloc(&ctx->gemm_pace, sizeof(unsigned int) * SC_GEMM_PACE_SLOTS) != cudaSuccess)
     ctx->gemm_pace = nullptr;
   // keep stream-ordered scratch inside the pool between calls (no trim at every sync)
   cudaMemPool_t pool;

@@ -10,12 +10,17 @@
 
 #include "../../include/spectralcluster_b200.h"
 
+constexpr int SC_GEMM_PACE_SLOTS = 16;
+
 struct sc_context {
   int device;
   int sm_count;
   size_t smem_optin;
   int cc_major, cc_minor;
-  unsigned int* gemm_pace;   // device counter for the GEMM producers' pacing checkpoints (one stream at a time)
+  // device counters for the GEMM producers' pacing checkpoints: a ring of SC_GEMM_PACE_SLOTS, one
+  // per launch in turn, so that GEMMs in flight on different streams (two threads running
+  // predict() on one context) do not count on each other's checkpoints
+  unsigned int* gemm_pace;
   int gemm_sm_limit;   // 0 = all SMs; otherwise the persistent GEMM leaves SMs to concurrent NCCL kernels
 };
 

@@ -30,6 +30,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -790,7 +791,8 @@ static int launch(const sc_context* ctx, const CUtensorMap& ah, const CUtensorMa
     pace_kb = (e && atoi(e) > 0) ? atoi(e) : PACE_KB;
   }
   if (ctx->gemm_pace && (K + BK - 1) / BK >= 2 * pace_kb && tiles > grid) {
-    pace = ctx->gemm_pace;
+    static std::atomic<unsigned int> pace_turn{0};
+    pace = ctx->gemm_pace + (pace_turn.fetch_add(1) % SC_GEMM_PACE_SLOTS);
     SC_CUDA(cudaMemsetAsync(pace, 0, sizeof(unsigned int), st));
   }
   cudaLaunchConfig_t cfg = {};
