@@ -8,6 +8,10 @@ from . import laplacian
 from . import refinement
 from . import spectral_clusterer
 
+AutoTune = autotune.AutoTune
+ConstraintName = constraint.ConstraintName
+ConstraintOptions = constraint.ConstraintOptions
+LaplacianType = laplacian.LaplacianType
 RefinementName = refinement.RefinementName
 RefinementOptions = refinement.RefinementOptions
 ThresholdType = refinement.ThresholdType

@@ -15,6 +15,24 @@ import typing
 import numpy as np
 
 
+class NaiveCentroid:
+  """One cluster of the naive algorithm as the reference exposes it (naive_clusterer.py:5-22):
+  the running mean `embedding` of its `count` members."""
+
+  def __init__(self, embedding: np.ndarray, count: int = 1):
+    self.embedding = embedding
+    self.count = count
+
+  def merge(self, embedding: np.ndarray):
+    total = self.count + 1
+    self.embedding = (self.embedding * self.count + embedding) / total
+    self.count = total
+
+  def cosine(self, embedding: np.ndarray) -> float:
+    norms = np.linalg.norm(self.embedding) * np.linalg.norm(embedding)
+    return float(np.dot(self.embedding, embedding) / norms)
+
+
 class NaiveClusterer:
   """Assign each embedding to the most similar running centroid, or open a new cluster."""
 
@@ -30,8 +48,11 @@ class NaiveClusterer:
     self._counts = []                      # members merged into each mean
 
   @property
-  def centroids(self):
-    return [] if self._means is None else list(self._means)
+  def centroids(self) -> typing.List[NaiveCentroid]:
+    """Snapshot of the clusters as NaiveCentroid objects (the reference keeps such a list)."""
+    if self._means is None:
+      return []
+    return [NaiveCentroid(row.copy(), count) for row, count in zip(self._means, self._counts)]
 
   def _open(self, embedding) -> int:
     row = np.asarray(embedding, dtype=np.float64)[None, :]

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _native as nat
 from . import autotune as autotune_lib
+from . import constraint as constraint_lib
 from . import custom_distance_kmeans
 from . import device as dev
 from . import fallback_clusterer
@@ -27,6 +28,8 @@ from . import utils
 
 AutoTune = autotune_lib.AutoTune
 AutoTuneProxy = autotune_lib.AutoTuneProxy
+ConstraintName = constraint_lib.ConstraintName
+ConstraintOptions = constraint_lib.ConstraintOptions
 FallbackOptions = fallback_clusterer.FallbackOptions
 LaplacianType = laplacian_lib.LaplacianType
 RefinementName = refinement.RefinementName

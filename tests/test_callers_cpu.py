@@ -114,3 +114,22 @@ def test_match_labels_known_answers():        # tests/multi_stage_clusterer_test
     ms.match_labels(np.array([0, 1]), np.array([0, 1]))
   with pytest.raises(ValueError):
     ms.MultiStageClusterer(scb.SpectralClusterer(max_spectral_size=50))
+
+
+def test_naive_centroid_surface_matches_reference_semantics():
+  """NaiveCentroid (naive_clusterer.py:5-22) and the aliases configs / spectral_clusterer export."""
+  from spectralcluster_b200 import configs, naive_clusterer, spectral_clusterer
+  c = naive_clusterer.NaiveCentroid(np.array([1.0, 0.0]))
+  c.merge(np.array([0.0, 1.0]))
+  assert c.count == 2 and np.allclose(c.embedding, [0.5, 0.5])
+  assert abs(c.cosine(np.array([1.0, 1.0])) - 1.0) < 1e-12
+  nc = naive_clusterer.NaiveClusterer(0.5)
+  labels = nc.predict(np.array([[1, 0], [0.9, 0.1], [0, 1.0], [0.1, 0.9]]))
+  assert labels.tolist() == [0, 0, 1, 1]
+  assert [k.count for k in nc.centroids] == [2, 2]
+  assert np.allclose(nc.centroids[0].embedding, [0.95, 0.05])
+  for name in ("AutoTune", "ConstraintName", "ConstraintOptions", "LaplacianType", "RefinementName",
+               "RefinementOptions", "ThresholdType", "SymmetrizeType", "SpectralClusterer"):
+    assert hasattr(configs, name), name
+  for name in ("ConstraintName", "ConstraintOptions", "AutoTune", "FallbackOptions", "LaplacianType"):
+    assert hasattr(spectral_clusterer, name), name
